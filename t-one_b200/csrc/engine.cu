@@ -1,0 +1,1225 @@
+// tone_engine: weights, per-stream state pool, step orchestration, CUDA graphs and the C ABI (include/tone_b200.h).
+//
+// The step follows the reference's Tone.forward_for_export (tone/nn/model.py:101-205) / SURVEY.md Appendix A.
+// Data layout in HBM (per slot = per stream, all persistent):
+//   pre   [80]            fp16   last 80 samples of the previous chunk                   (A1)
+//   feat  [50][64]        bf16   RMSNorm'ed log-mel rows: 10 cached + F new              (A2, conv0 input)
+//   x1    [48][44][32]    bf16   conv0 output, channels-last: 8 cached + F new rows      (A2, conv1 input)
+//   kv14  [44][384]       bf16   layer-14 attention input rows: 15 cached + T2 new       (A5)
+//   kv15  [44][384]       bf16   layer-15 attention input rows: 30 cached + T new        (A5)
+//   conv  [16][30][384]   bf16   depthwise-conv caches, time-major                       (A4.3)
+//   red   [384]           fp32   last layer-6 output frame                               (A4 reduction)
+//   len   int32                  mhsa_len
+// Between steps the carried rows sit at the END of [cache | new] (rows [F,F+10) of feat, ...); the next step's
+// begin_step_kernel rolls them to the front.  Import/export use the same convention.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tone_b200.h"
+#include "gemm_ref.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace tone;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess) return fail(TONE_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ host bf16/fp16
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline float h2f(uint16_t h) {
+  __half_raw r;
+  r.x = h;
+  return __half2float(__half(r));
+}
+static inline uint16_t f2h(float f) {
+  __half_raw r = static_cast<__half_raw>(__float2half_rn(f));
+  return r.x;
+}
+
+// ------------------------------------------------------------------------------------------------ model constants
+static const int N_LAYERS = 16, D_FF = 1536, N_CLASSES = 35, DEC_PAD = 48;
+static const int SUB_OUT = 2176;  // 34 * 64
+static const bool RECOMPUTE[16] = {true, false, false, false, false, false, false, true,
+                                   false, false, false, false, false, false, true, true};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct WeightMat {      // a bf16 [N][K] matrix on the device with its TMA map (box 64 x BN)
+  bf16* ptr = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap map;
+};
+
+struct LayerW {
+  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw2;
+  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw2_b;
+  float *n_ff1, *n_att, *n_conv, *n_ff2, *n_out;
+  float *qln_w, *qln_b, *kln_w, *kln_b;
+  float *dw_w, *dw_b;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct tone_engine {
+  tone_config cfg;
+  int C, F, T, T2;
+  cudaStream_t stream = nullptr;
+  PFN_encodeTiled encode = nullptr;
+  std::map<std::string, HostTensor> host_w;
+  bool finalized = false;
+
+  // arenas
+  char* w_arena = nullptr;
+  size_t w_cap = 0, w_used = 0;
+  std::vector<void*> allocs;
+
+  // weights
+  WeightMat conv0_w, conv1_w, out_w, red_pw, dec_w;
+  float *conv0_alpha, *conv0_beta, *conv1_alpha, *conv1_beta, *pre_norm_g, *out_norm_g;
+  float *red_dw_w, *red_dw_b, *red_pw_b, *dec_b;
+  LayerW L[16];
+  float *basis, *mel_w, *rope_cos, *rope_sin;
+  int* mel_start;
+  unsigned char* mel_bin;
+
+  // state pool
+  __half* st_pre;
+  bf16 *st_feat, *st_x1, *st_kv14, *st_kv15, *st_conv;
+  float* st_red;
+  int* st_len;
+  std::vector<int> free_slots;
+  std::vector<char> slot_used;
+
+  // step scratch
+  int rows_alloc;
+  int *d_slots, *d_pcm, *d_len_in, *d_tokens;
+  float *r_full, *r_red, *qkv, *P, *logprobs;
+  bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
+  CUtensorMap m_feat, m_x1, m_kv14, m_kv15, m_n, m_h, m_ctx, m_e, m_c1, m_mred;
+
+  // pinned staging
+  int *p_slots, *p_pcm, *p_tokens;
+  float* p_logprobs;
+
+  std::unordered_map<int, cudaGraphExec_t> graphs;
+  int launches = 0, launches_per_step = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+template <typename Tp>
+static int dev_alloc(tone_engine* e, Tp** p, size_t n) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n * sizeof(Tp), 256)));
+  CK(cudaMemset(q, 0, std::max<size_t>(n * sizeof(Tp), 256)));
+  e->allocs.push_back(q);
+  *p = (Tp*)q;
+  return 0;
+}
+static void* arena_take(tone_engine* e, size_t bytes) {
+  size_t off = (e->w_used + 255) & ~size_t(255);
+  if (off + bytes > e->w_cap) return nullptr;
+  e->w_used = off + bytes;
+  return e->w_arena + off;
+}
+static int upload_f32(tone_engine* e, const std::vector<float>& v, float** out) {
+  void* p = arena_take(e, v.size() * 4);
+  if (!p) return fail(TONE_ENOMEM, "weight arena exhausted");
+  CK(cudaMemcpy(p, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  *out = (float*)p;
+  return 0;
+}
+static int make_map(tone_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool weight) {
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B,
+                         weight ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TONE_ECUDA, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+  return 0;
+}
+static int make_map_2d(tone_engine* e, CUtensorMap* m, void* base, uint64_t rows, uint64_t K, uint32_t box_rows,
+                       bool weight) {
+  uint64_t dims[2] = {K, rows}, st[1] = {K * 2};
+  uint32_t box[2] = {64, box_rows};
+  return make_map(e, m, base, 2, dims, st, box, weight);
+}
+static int upload_mat(tone_engine* e, const std::vector<float>& w, int N, int K, int box_rows, WeightMat* out) {
+  std::vector<uint16_t> b((size_t)N * K);
+  for (size_t i = 0; i < b.size(); ++i) b[i] = f2bf(w[i]);
+  void* p = arena_take(e, b.size() * 2);
+  if (!p) return fail(TONE_ENOMEM, "weight arena exhausted");
+  CK(cudaMemcpy(p, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+  out->ptr = (bf16*)p;
+  out->N = N;
+  out->K = K;
+  return make_map_2d(e, &out->map, p, N, K, box_rows, true);
+}
+static const HostTensor* W(tone_engine* e, const std::string& name) {
+  auto it = e->host_w.find(name);
+  return it == e->host_w.end() ? nullptr : &it->second;
+}
+#define NEEDW(var, name)                                                         \
+  const HostTensor* var = W(e, name);                                            \
+  if (!var) return fail(TONE_ESTATE, "weight '%s' was not loaded", std::string(name).c_str());
+
+// rows of Wa / Wb interleaved in blocks of HW so that one BN = 2*HW output tile holds matching columns
+static std::vector<float> interleave_rows(const std::vector<float>& a, const std::vector<float>& b, int Nh, int K,
+                                          int HW) {
+  std::vector<float> o((size_t)2 * Nh * K);
+  for (int t = 0; t < Nh / HW; ++t)
+    for (int r = 0; r < HW; ++r) {
+      memcpy(&o[((size_t)t * 2 * HW + r) * K], &a[((size_t)t * HW + r) * K], (size_t)K * 4);
+      memcpy(&o[((size_t)t * 2 * HW + HW + r) * K], &b[((size_t)t * HW + r) * K], (size_t)K * 4);
+    }
+  return o;
+}
+static std::vector<float> concat(std::initializer_list<const std::vector<float>*> parts) {
+  std::vector<float> o;
+  for (auto p : parts) o.insert(o.end(), p->begin(), p->end());
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+static const int BN_SWIGLU = 128, BN_RESID = 32, BN_GLU = 64, BN_STORE = 64, BN_CONV = 128, BN_KV = 64;
+
+extern "C" const char* tone_last_error(void) { return g_err; }
+
+extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
+  if (!cfg || !out) return fail(TONE_EINVAL, "null argument");
+  if (cfg->chunk_samples != 2400 && cfg->chunk_samples != 3200)
+    return fail(TONE_EINVAL, "chunk_samples must be 2400 (300 ms) or 3200 (400 ms), got %d", cfg->chunk_samples);
+  if (cfg->max_slots < 1 || cfg->max_batch < 1 || cfg->max_batch > cfg->max_slots)
+    return fail(TONE_EINVAL, "need 1 <= max_batch <= max_slots");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(TONE_EINVAL, "device %d of %d", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(TONE_ECUDA, "this library is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+
+  tone_engine* e = new tone_engine();
+  e->cfg = *cfg;
+  e->C = cfg->chunk_samples;
+  e->F = e->C / HOP;
+  e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
+  e->T2 = (e->T + 1 - 3) / 2 + 1;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail(TONE_ECUDA, "cuTensorMapEncodeTiled not available");
+    e->encode = (PFN_encodeTiled)fn;
+  }
+  // weight arena: ~72M params in bf16 + expanded conv matrices + fp32 vectors
+  e->w_cap = (size_t)200 << 20;
+  CK(cudaMalloc((void**)&e->w_arena, e->w_cap));
+  CK(cudaMemset(e->w_arena, 0, e->w_cap));
+
+  const size_t S = cfg->max_slots;
+  int rc = 0;
+  rc |= dev_alloc(e, &e->st_pre, S * HOP);
+  rc |= dev_alloc(e, &e->st_feat, S * FEAT_ROWS_MAX * N_MELS);
+  rc |= dev_alloc(e, &e->st_x1, S * X1_ROWS_MAX * X1_ROW);
+  rc |= dev_alloc(e, &e->st_kv14, S * KV_ROWS_MAX * D_MODEL);
+  rc |= dev_alloc(e, &e->st_kv15, S * KV_ROWS_MAX * D_MODEL);
+  rc |= dev_alloc(e, &e->st_conv, S * N_LAYERS * CONV_S * D_MODEL);
+  rc |= dev_alloc(e, &e->st_red, S * D_MODEL);
+  rc |= dev_alloc(e, &e->st_len, S);
+  if (rc) return rc;
+  e->slot_used.assign(S, 0);
+  for (int i = (int)S - 1; i >= 0; --i) e->free_slots.push_back(i);
+
+  const size_t Bm = cfg->max_batch;
+  e->rows_alloc = (int)(((Bm * MAX_T + 127) / 128) * 128);
+  const size_t R = e->rows_alloc;
+  rc |= dev_alloc(e, &e->d_slots, Bm);
+  rc |= dev_alloc(e, &e->d_pcm, Bm * e->C);
+  rc |= dev_alloc(e, &e->d_len_in, Bm);
+  rc |= dev_alloc(e, &e->d_tokens, R);
+  rc |= dev_alloc(e, &e->r_full, R * D_MODEL);
+  rc |= dev_alloc(e, &e->r_red, R * D_MODEL);
+  rc |= dev_alloc(e, &e->qkv, std::max(R * 3 * D_MODEL, Bm * (MHSA_S + MAX_T) * 2 * D_MODEL + R * D_MODEL));
+  rc |= dev_alloc(e, &e->P, Bm * N_HEADS * MAX_T * (MHSA_S + MAX_T));
+  rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
+  rc |= dev_alloc(e, &e->n, R * D_MODEL);
+  rc |= dev_alloc(e, &e->h, R * D_FF);
+  rc |= dev_alloc(e, &e->ctx, R * D_MODEL);
+  rc |= dev_alloc(e, &e->g, R * D_MODEL);
+  rc |= dev_alloc(e, &e->ebuf, R * D_MODEL);
+  rc |= dev_alloc(e, &e->c1, R * SUB_OUT);
+  rc |= dev_alloc(e, &e->m_red, R * D_FF);
+  if (rc) return rc;
+  CK(cudaMallocHost((void**)&e->p_slots, Bm * 4));
+  CK(cudaMallocHost((void**)&e->p_pcm, Bm * e->C * 4));
+  CK(cudaMallocHost((void**)&e->p_tokens, Bm * MAX_T * 4));
+  CK(cudaMallocHost((void**)&e->p_logprobs, Bm * MAX_T * N_CLASSES * 4));
+
+  // activation-side tensor maps
+  {
+    uint64_t d[3] = {N_MELS, FEAT_ROWS_MAX, S}, s[2] = {N_MELS * 2, (uint64_t)FEAT_ROWS_MAX * N_MELS * 2};
+    uint32_t bx[3] = {64, (uint32_t)e->F, 1};
+    if ((rc = make_map(e, &e->m_feat, e->st_feat, 3, d, s, bx, false))) return rc;
+  }
+  {  // x1 as [slot][16 row triples][3 rows][1408]: conv1 frame t, kernel row kt reads row 3t+kt = triple t+kt/3, row kt%3
+    uint64_t d[4] = {X1_ROW, 3, X1_ROWS_MAX / 3, S};
+    uint64_t s[3] = {X1_ROW * 2, 3 * X1_ROW * 2, (uint64_t)X1_ROWS_MAX * X1_ROW * 2};
+    uint32_t bx[4] = {64, 1, (uint32_t)e->T, 1};
+    if ((rc = make_map(e, &e->m_x1, e->st_x1, 4, d, s, bx, false))) return rc;
+  }
+  {
+    uint64_t d[3] = {D_MODEL, KV_ROWS_MAX, S}, s[2] = {D_MODEL * 2, (uint64_t)KV_ROWS_MAX * D_MODEL * 2};
+    uint32_t b14[3] = {64, (uint32_t)(MHSA_S / 2 + e->T2), 1}, b15[3] = {64, (uint32_t)(MHSA_S + e->T), 1};
+    if ((rc = make_map(e, &e->m_kv14, e->st_kv14, 3, d, s, b14, false))) return rc;
+    if ((rc = make_map(e, &e->m_kv15, e->st_kv15, 3, d, s, b15, false))) return rc;
+  }
+  if ((rc = make_map_2d(e, &e->m_n, e->n, R, D_MODEL, 128, false))) return rc;
+  if ((rc = make_map_2d(e, &e->m_h, e->h, R, D_FF, 128, false))) return rc;
+  if ((rc = make_map_2d(e, &e->m_ctx, e->ctx, R, D_MODEL, 128, false))) return rc;
+  if ((rc = make_map_2d(e, &e->m_e, e->ebuf, R, D_MODEL, 128, false))) return rc;
+  if ((rc = make_map_2d(e, &e->m_c1, e->c1, R, SUB_OUT, 128, false))) return rc;
+  if ((rc = make_map_2d(e, &e->m_mred, e->m_red, R, D_FF, 128, false))) return rc;
+
+  CK((configure_gemm_tc<G_SWIGLU, BN_SWIGLU>()));
+  CK((configure_gemm_tc<G_RESID, BN_RESID>()));
+  CK((configure_gemm_tc<G_GLU, BN_GLU>()));
+  CK((configure_gemm_tc<G_STORE_F32, BN_STORE>()));
+  CK((configure_gemm_tc<G_STORE_F32, 32>()));
+  CK((configure_gemm_tc<G_STORE_F32, 128>()));
+  CK((configure_gemm_tc<G_CONV0, BN_CONV>()));
+  CK((configure_gemm_tc<G_CONV1, BN_CONV>()));
+  CK((configure_gemm_tc<G_KV, BN_KV>()));
+  CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
+  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  *out = e;
+  return TONE_OK;
+}
+
+extern "C" void tone_destroy(tone_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : e->allocs) cudaFree(p);
+  cudaFree(e->w_arena);
+  cudaFreeHost(e->p_slots);
+  cudaFreeHost(e->p_pcm);
+  cudaFreeHost(e->p_tokens);
+  cudaFreeHost(e->p_logprobs);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int tone_get_info(const tone_engine* e, tone_info* o) {
+  if (!e || !o) return fail(TONE_EINVAL, "null argument");
+  o->chunk_samples = e->C;
+  o->frames_out = e->T;
+  o->n_classes = N_CLASSES;
+  o->state_size = TONE_STATE_SIZE;
+  o->max_slots = e->cfg.max_slots;
+  o->max_batch = e->cfg.max_batch;
+  o->launches_per_step = e->launches_per_step;
+  o->n_taps = 1 + N_LAYERS;
+  o->state_bytes_per_slot = (int64_t)HOP * 2 + FEAT_ROWS_MAX * N_MELS * 2 + (int64_t)X1_ROWS_MAX * X1_ROW * 2 +
+                            2LL * KV_ROWS_MAX * D_MODEL * 2 + (int64_t)N_LAYERS * CONV_S * D_MODEL * 2 + D_MODEL * 4 + 4;
+  o->weight_bytes = (int64_t)e->w_used;
+  return TONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+extern "C" int tone_load_weight(tone_engine* e, const char* name, const float* data, const int64_t* shape,
+                                int32_t ndim) {
+  if (!e || !name || !data || !shape || ndim < 1 || ndim > 4) return fail(TONE_EINVAL, "bad argument");
+  if (e->finalized) return fail(TONE_ESTATE, "weights already finalized");
+  std::string nm(name);
+  if (nm.rfind("tone.", 0) == 0) nm = nm.substr(5);
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 1) return fail(TONE_EINVAL, "bad shape for %s", name);
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(data, data + n);
+  e->host_w[nm] = std::move(t);
+  return TONE_OK;
+}
+
+static int expect_shape(const HostTensor* t, const char* name, std::initializer_list<int64_t> s) {
+  std::vector<int64_t> v(s);
+  if (t->shape != v) return fail(TONE_EINVAL, "weight '%s' has an unexpected shape", name);
+  return 0;
+}
+
+static int bn_fold(tone_engine* e, const std::string& bn, const std::vector<float>& conv_bias, int n,
+                   std::vector<float>& alpha, std::vector<float>& beta) {
+  NEEDW(w, bn + "weight");
+  NEEDW(b, bn + "bias");
+  NEEDW(m, bn + "running_mean");
+  NEEDW(v, bn + "running_var");
+  alpha.resize(n);
+  beta.resize(n);
+  for (int i = 0; i < n; ++i) {
+    float a = w->data[i] / sqrtf(v->data[i] + 1e-5f);  // BatchNorm eval, eps 1e-5
+    alpha[i] = a;
+    beta[i] = (conv_bias[i] - m->data[i]) * a + b->data[i];
+  }
+  return 0;
+}
+
+static int finalize_frontend(tone_engine* e) {
+  // fused (pre-emphasis x symmetric Hann x DFT-160) basis, stored [j][k] (feats.py:66-80)
+  const double PI = 3.14159265358979323846;
+  std::vector<double> basis((size_t)162 * WIN);
+  for (int k = 0; k < N_BINS; ++k)
+    for (int j = 0; j < WIN; ++j) {
+      double hann = 0.5 - 0.5 * cos(2.0 * PI * j / (WIN - 1));
+      double ang = 2.0 * PI * (double)k * j / WIN;
+      basis[(size_t)k * WIN + j] = cos(ang) * hann;
+      basis[(size_t)(N_BINS + k) * WIN + j] = -sin(ang) * hann;
+    }
+  std::vector<float> bt((size_t)WIN * 162);
+  for (int k = 0; k < 162; ++k)
+    for (int j = 0; j < WIN; ++j) {
+      double v = basis[(size_t)k * WIN + j];
+      if (j + 1 < WIN) v -= 0.97 * basis[(size_t)k * WIN + j + 1];
+      if (j == 0) v -= 0.97 * basis[(size_t)k * WIN];
+      bt[(size_t)j * 162 + k] = (float)v;
+    }
+  int rc = upload_f32(e, bt, &e->basis);
+  if (rc) return rc;
+  // slaney mel filterbank in CSR form (feats.py:82-93; torchaudio melscale_fbanks, slaney scale + norm)
+  auto hz2mel = [](double f) {
+    const double f_sp = 200.0 / 3, logstep = log(6.4) / 27.0;
+    return f >= 1000.0 ? 1000.0 / f_sp + log(f / 1000.0) / logstep : f / f_sp;
+  };
+  auto mel2hz = [](double m) {
+    const double f_sp = 200.0 / 3, logstep = log(6.4) / 27.0, mlm = 1000.0 / f_sp;
+    return m >= mlm ? 1000.0 * exp(logstep * (m - mlm)) : f_sp * m;
+  };
+  std::vector<double> fpts(N_MELS + 2);
+  const double m0 = hz2mel(0.0), m1 = hz2mel(4000.0);
+  for (int i = 0; i < N_MELS + 2; ++i) fpts[i] = mel2hz(m0 + (m1 - m0) * i / (N_MELS + 1));
+  std::vector<int> start(N_MELS + 1, 0);
+  std::vector<unsigned char> bins;
+  std::vector<float> wts;
+  for (int m = 0; m < N_MELS; ++m) {
+    start[m] = (int)bins.size();
+    for (int k = 0; k < N_BINS; ++k) {
+      double fr = 4000.0 * k / (N_BINS - 1);
+      double down = (fr - fpts[m]) / (fpts[m + 1] - fpts[m]);
+      double up = (fpts[m + 2] - fr) / (fpts[m + 2] - fpts[m + 1]);
+      double v = std::max(0.0, std::min(down, up)) * (2.0 / (fpts[m + 2] - fpts[m]));
+      if (v > 0.0) {
+        bins.push_back((unsigned char)k);
+        wts.push_back((float)v);
+      }
+    }
+  }
+  start[N_MELS] = (int)bins.size();
+  if ((rc = upload_f32(e, wts, &e->mel_w))) return rc;
+  void* p = arena_take(e, start.size() * 4);
+  CK(cudaMemcpy(p, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+  e->mel_start = (int*)p;
+  p = arena_take(e, bins.size());
+  CK(cudaMemcpy(p, bins.data(), bins.size(), cudaMemcpyHostToDevice));
+  e->mel_bin = (unsigned char*)p;
+  // RoPE tables for positions -30 .. 12 (submodules.py:117-139): angle = pos * 10000^(-2i/32), fp32
+  std::vector<float> rc_((size_t)(MHSA_S + MAX_T) * 16), rs_((size_t)(MHSA_S + MAX_T) * 16);
+  for (int p_ = 0; p_ < MHSA_S + MAX_T; ++p_)
+    for (int i = 0; i < 16; ++i) {
+      float inv = 1.0f / powf(10000.0f, (float)(2 * i) / 32.0f);
+      float ang = (float)(p_ - MHSA_S) * inv;
+      rc_[p_ * 16 + i] = cosf(ang);
+      rs_[p_ * 16 + i] = sinf(ang);
+    }
+  if ((rc = upload_f32(e, rc_, &e->rope_cos))) return rc;
+  return upload_f32(e, rs_, &e->rope_sin);
+}
+
+static int finalize_pre_encode(tone_engine* e) {
+  const std::string P = "encoder.pre_encode.";
+  int rc;
+  NEEDW(pn, P + "pre_norm.weight");
+  if ((rc = upload_f32(e, pn->data, &e->pre_norm_g))) return rc;
+  NEEDW(on, P + "out_norm.weight");
+  if ((rc = upload_f32(e, on->data, &e->out_norm_g))) return rc;
+  // conv0 (32,1,11,21) as a banded [f*32+o][kt*64+fin] matrix: the GEMM row is a frame, K walks 11 feature rows
+  NEEDW(w0, P + "conv.0.0.weight");
+  NEEDW(b0, P + "conv.0.0.bias");
+  if ((rc = expect_shape(w0, "conv.0.0.weight", {32, 1, 11, 21}))) return rc;
+  {
+    std::vector<float> t((size_t)1408 * 704, 0.f);
+    for (int f = 0; f < 44; ++f)
+      for (int o = 0; o < 32; ++o)
+        for (int kt = 0; kt < 11; ++kt)
+          for (int kf = 0; kf < 21; ++kf)
+            t[(size_t)(f * 32 + o) * 704 + kt * 64 + f + kf] = w0->data[((size_t)o * 11 + kt) * 21 + kf];
+    if ((rc = upload_mat(e, t, 1408, 704, BN_CONV, &e->conv0_w))) return rc;
+    std::vector<float> al, be;
+    if ((rc = bn_fold(e, P + "conv.0.1.", b0->data, 32, al, be))) return rc;
+    if ((rc = upload_f32(e, al, &e->conv0_alpha))) return rc;
+    if ((rc = upload_f32(e, be, &e->conv0_beta))) return rc;
+  }
+  // conv1 (64,32,11,11): two adjacent output positions j in {0,1} share a 12-position window:
+  //   W2[j*64+o][kt*384 + d*32 + c] = w[o][c][kt][d-j]  for 0 <= d-j < 11
+  NEEDW(w1, P + "conv.1.0.weight");
+  NEEDW(b1, P + "conv.1.0.bias");
+  if ((rc = expect_shape(w1, "conv.1.0.weight", {64, 32, 11, 11}))) return rc;
+  {
+    const int K = 11 * 384;
+    std::vector<float> t((size_t)128 * K, 0.f);
+    for (int j = 0; j < 2; ++j)
+      for (int o = 0; o < 64; ++o)
+        for (int kt = 0; kt < 11; ++kt)
+          for (int kf = 0; kf < 11; ++kf)
+            for (int c = 0; c < 32; ++c)
+              t[(size_t)(j * 64 + o) * K + kt * 384 + (kf + j) * 32 + c] =
+                  w1->data[(((size_t)o * 32 + c) * 11 + kt) * 11 + kf];
+    if ((rc = upload_mat(e, t, 128, K, BN_CONV, &e->conv1_w))) return rc;
+    std::vector<float> al, be;
+    if ((rc = bn_fold(e, P + "conv.1.1.", b1->data, 64, al, be))) return rc;
+    if ((rc = upload_f32(e, al, &e->conv1_alpha))) return rc;
+    if ((rc = upload_f32(e, be, &e->conv1_beta))) return rc;
+  }
+  // out Linear (384, 2176): reference flattens o*34+f (conformer_blocks.py:649); our rows are f*64+o
+  NEEDW(wo, P + "out.weight");
+  if ((rc = expect_shape(wo, "out.weight", {384, 2176}))) return rc;
+  {
+    std::vector<float> t((size_t)384 * SUB_OUT);
+    for (int n = 0; n < 384; ++n)
+      for (int o = 0; o < 64; ++o)
+        for (int f = 0; f < 34; ++f) t[(size_t)n * SUB_OUT + f * 64 + o] = wo->data[(size_t)n * SUB_OUT + o * 34 + f];
+    if ((rc = upload_mat(e, t, 384, SUB_OUT, BN_STORE, &e->out_w))) return rc;
+  }
+  return 0;
+}
+
+static int finalize_layer(tone_engine* e, int l) {
+  const std::string Lp = "encoder.layers." + std::to_string(l) + ".";
+  LayerW& L = e->L[l];
+  int rc;
+  auto vec = [&](const std::string& nm, float** out) -> int {
+    NEEDW(t, Lp + nm);
+    return upload_f32(e, t->data, out);
+  };
+  if ((rc = vec("norm_feed_forward1.weight", &L.n_ff1))) return rc;
+  if ((rc = vec("norm_self_att.weight", &L.n_att))) return rc;
+  if ((rc = vec("norm_conv.weight", &L.n_conv))) return rc;
+  if ((rc = vec("norm_feed_forward2.weight", &L.n_ff2))) return rc;
+  if ((rc = vec("norm_out.weight", &L.n_out))) return rc;
+  for (int k = 0; k < 2; ++k) {
+    const std::string ff = Lp + (k == 0 ? "feed_forward1." : "feed_forward2.");
+    NEEDW(w1, ff + "linear1.weight");
+    NEEDW(b1, ff + "linear1.bias");
+    NEEDW(wv, ff + "linearv.weight");
+    NEEDW(bv, ff + "linearv.bias");
+    NEEDW(w2, ff + "linear2.weight");
+    NEEDW(b2, ff + "linear2.bias");
+    if ((rc = expect_shape(w1, "linear1.weight", {D_FF, D_MODEL}))) return rc;
+    if ((rc = expect_shape(w2, "linear2.weight", {D_MODEL, D_FF}))) return rc;
+    std::vector<float> up = interleave_rows(w1->data, wv->data, D_FF, D_MODEL, BN_SWIGLU / 2);
+    std::vector<float> upb = interleave_rows(b1->data, bv->data, D_FF, 1, BN_SWIGLU / 2);
+    WeightMat* mu = k == 0 ? &L.ff1_up : &L.ff2_up;
+    WeightMat* md = k == 0 ? &L.ff1_down : &L.ff2_down;
+    if ((rc = upload_mat(e, up, 2 * D_FF, D_MODEL, BN_SWIGLU, mu))) return rc;
+    if ((rc = upload_f32(e, upb, k == 0 ? &L.ff1_up_b : &L.ff2_up_b))) return rc;
+    if ((rc = upload_mat(e, w2->data, D_MODEL, D_FF, BN_RESID, md))) return rc;
+    if ((rc = upload_f32(e, b2->data, k == 0 ? &L.ff1_down_b : &L.ff2_down_b))) return rc;
+  }
+  const std::string A = Lp + "self_attn.";
+  NEEDW(wv, A + "linear_v.weight");
+  NEEDW(bv, A + "linear_v.bias");
+  NEEDW(wo, A + "linear_out.weight");
+  NEEDW(bo, A + "linear_out.bias");
+  if ((rc = upload_mat(e, wo->data, D_MODEL, D_MODEL, BN_RESID, &L.wo))) return rc;
+  if ((rc = upload_f32(e, bo->data, &L.wo_b))) return rc;
+  if (RECOMPUTE[l]) {
+    NEEDW(wq, A + "linear_q.weight");
+    NEEDW(bq, A + "linear_q.bias");
+    NEEDW(wk, A + "linear_k.weight");
+    NEEDW(bk, A + "linear_k.bias");
+    if (l < 14) {  // q | k | v on the same T rows
+      if ((rc = upload_mat(e, concat({&wq->data, &wk->data, &wv->data}), 3 * D_MODEL, D_MODEL, BN_STORE, &L.qkv)))
+        return rc;
+      if ((rc = upload_f32(e, concat({&bq->data, &bk->data, &bv->data}), &L.qkv_b))) return rc;
+    } else {       // q on the T new rows, k | v on the S+T [cache | new] rows
+      if ((rc = upload_mat(e, wq->data, D_MODEL, D_MODEL, BN_STORE, &L.q))) return rc;
+      if ((rc = upload_f32(e, bq->data, &L.q_b))) return rc;
+      if ((rc = upload_mat(e, concat({&wk->data, &wv->data}), 2 * D_MODEL, D_MODEL, BN_KV, &L.kv))) return rc;
+      if ((rc = upload_f32(e, concat({&bk->data, &bv->data}), &L.kv_b))) return rc;
+    }
+    NEEDW(qw, A + "q_ln.weight");
+    NEEDW(qb, A + "q_ln.bias");
+    NEEDW(kw, A + "k_ln.weight");
+    NEEDW(kb, A + "k_ln.bias");
+    if ((rc = upload_f32(e, qw->data, &L.qln_w))) return rc;
+    if ((rc = upload_f32(e, qb->data, &L.qln_b))) return rc;
+    if ((rc = upload_f32(e, kw->data, &L.kln_w))) return rc;
+    if ((rc = upload_f32(e, kb->data, &L.kln_b))) return rc;
+  } else {
+    if ((rc = upload_mat(e, wv->data, D_MODEL, D_MODEL, BN_STORE, &L.qkv))) return rc;
+    if ((rc = upload_f32(e, bv->data, &L.qkv_b))) return rc;
+  }
+  // conv module: pw1 rows [0,384) = a, [384,768) = b (GLU = a * sigmoid(b), conformer_blocks.py:422)
+  const std::string Cp = Lp + "conv.";
+  NEEDW(p1, Cp + "pointwise_conv1.weight");
+  NEEDW(p1b, Cp + "pointwise_conv1.bias");
+  {
+    std::vector<float> a(p1->data.begin(), p1->data.begin() + (size_t)D_MODEL * D_MODEL);
+    std::vector<float> b(p1->data.begin() + (size_t)D_MODEL * D_MODEL, p1->data.end());
+    std::vector<float> ab(p1b->data.begin(), p1b->data.begin() + D_MODEL);
+    std::vector<float> bb(p1b->data.begin() + D_MODEL, p1b->data.end());
+    if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, BN_GLU / 2), 2 * D_MODEL, D_MODEL, BN_GLU, &L.pw1)))
+      return rc;
+    if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, BN_GLU / 2), &L.pw1_b))) return rc;
+  }
+  NEEDW(dw, Cp + "depthwise_conv.conv.weight");
+  NEEDW(dwb, Cp + "depthwise_conv.conv.bias");
+  {
+    std::vector<float> al, be;
+    if ((rc = bn_fold(e, Cp + "batch_norm.", dwb->data, D_MODEL, al, be))) return rc;
+    std::vector<float> t((size_t)31 * D_MODEL);
+    for (int c = 0; c < D_MODEL; ++c)
+      for (int j = 0; j < 31; ++j) t[(size_t)j * D_MODEL + c] = dw->data[(size_t)c * 31 + j] * al[c];
+    if ((rc = upload_f32(e, t, &L.dw_w))) return rc;
+    if ((rc = upload_f32(e, be, &L.dw_b))) return rc;
+  }
+  NEEDW(p2, Cp + "pointwise_conv2.weight");
+  NEEDW(p2b, Cp + "pointwise_conv2.bias");
+  if ((rc = upload_mat(e, p2->data, D_MODEL, D_MODEL, BN_RESID, &L.pw2))) return rc;
+  if ((rc = upload_f32(e, p2b->data, &L.pw2_b))) return rc;
+  return 0;
+}
+
+extern "C" int tone_finalize_weights(tone_engine* e) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  if (e->finalized) return fail(TONE_ESTATE, "weights already finalized");
+  CK(cudaSetDevice(e->cfg.device));
+  int rc;
+  if ((rc = finalize_frontend(e))) return rc;
+  if ((rc = finalize_pre_encode(e))) return rc;
+  for (int l = 0; l < N_LAYERS; ++l)
+    if ((rc = finalize_layer(e, l))) return rc;
+  const std::string R = "encoder.temportal_reduction.";
+  NEEDW(rw, R + "conv.weight");
+  NEEDW(rb, R + "conv.bias");
+  NEEDW(pw, R + "conv_pw.weight");
+  NEEDW(pb, R + "conv_pw.bias");
+  if ((rc = expect_shape(rw, "reduction conv.weight", {4 * D_MODEL, 1, 3}))) return rc;
+  if ((rc = upload_f32(e, rw->data, &e->red_dw_w))) return rc;
+  if ((rc = upload_f32(e, rb->data, &e->red_dw_b))) return rc;
+  if ((rc = upload_mat(e, pw->data, D_MODEL, D_FF, BN_STORE, &e->red_pw))) return rc;
+  if ((rc = upload_f32(e, pb->data, &e->red_pw_b))) return rc;
+  NEEDW(dw, "decoder.decoder_layers.0.weight");
+  NEEDW(db, "decoder.decoder_layers.0.bias");
+  if ((rc = expect_shape(dw, "decoder weight", {N_CLASSES, D_MODEL, 1}))) return rc;
+  {
+    std::vector<float> t((size_t)DEC_PAD * D_MODEL, 0.f);
+    memcpy(t.data(), dw->data.data(), (size_t)N_CLASSES * D_MODEL * 4);
+    if ((rc = upload_mat(e, t, DEC_PAD, D_MODEL, DEC_PAD, &e->dec_w))) return rc;
+    if ((rc = upload_f32(e, db->data, &e->dec_b))) return rc;
+  }
+  e->host_w.clear();
+  e->finalized = true;
+  return TONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slots
+extern "C" int tone_reset_slots(tone_engine* e, int32_t n, const int32_t* slots) {
+  if (!e || !slots || n < 0) return fail(TONE_EINVAL, "bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < n; ++i) {
+    const size_t s = slots[i];
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slots[i]);
+    CK(cudaMemsetAsync(e->st_pre + s * HOP, 0, HOP * 2, e->stream));
+    CK(cudaMemsetAsync(e->st_feat + s * FEAT_ROWS_MAX * N_MELS, 0, FEAT_ROWS_MAX * N_MELS * 2, e->stream));
+    CK(cudaMemsetAsync(e->st_x1 + s * X1_ROWS_MAX * X1_ROW, 0, (size_t)X1_ROWS_MAX * X1_ROW * 2, e->stream));
+    CK(cudaMemsetAsync(e->st_kv14 + s * KV_ROWS_MAX * D_MODEL, 0, KV_ROWS_MAX * D_MODEL * 2, e->stream));
+    CK(cudaMemsetAsync(e->st_kv15 + s * KV_ROWS_MAX * D_MODEL, 0, KV_ROWS_MAX * D_MODEL * 2, e->stream));
+    CK(cudaMemsetAsync(e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, 0, (size_t)N_LAYERS * CONV_S * D_MODEL * 2,
+                       e->stream));
+    CK(cudaMemsetAsync(e->st_red + s * D_MODEL, 0, D_MODEL * 4, e->stream));
+    CK(cudaMemsetAsync(e->st_len + s, 0, 4, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return TONE_OK;
+}
+
+extern "C" int tone_alloc_slots(tone_engine* e, int32_t n, int32_t* out) {
+  if (!e || !out || n < 0) return fail(TONE_EINVAL, "bad argument");
+  if ((size_t)n > e->free_slots.size())
+    return fail(TONE_ENOMEM, "%d slots requested, %zu free of %d", n, e->free_slots.size(), e->cfg.max_slots);
+  for (int i = 0; i < n; ++i) {
+    out[i] = e->free_slots.back();
+    e->free_slots.pop_back();
+    e->slot_used[out[i]] = 1;
+  }
+  return tone_reset_slots(e, n, out);
+}
+
+extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slots) {
+  if (!e || !slots || n < 0) return fail(TONE_EINVAL, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
+      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
+    e->slot_used[slots[i]] = 0;
+    e->free_slots.push_back(slots[i]);
+  }
+  return TONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ the step
+template <int KIND, int BN>
+static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const WeightMat& w, GemmArgs a, int m_tiles,
+                int n_tiles, int ref_rows, int ref_cols) {
+  a.W = w.ptr;
+  a.ldw = w.K;
+  cudaError_t err;
+  if (e->cfg.gemm_impl == 0) err = launch_gemm_tc<KIND, BN>(st, tmA, w.map, a, m_tiles, n_tiles);
+  else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols);
+  e->launches++;
+  if (err != cudaSuccess) return fail(TONE_ECUDA, "gemm kind %d launch: %s", KIND, cudaGetErrorString(err));
+  return 0;
+}
+
+static GemmArgs dense_args(int M, int K, const bf16* A, void* out, int ldo, const float* bias, float scale) {
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M;
+  a.nk = K / 64;
+  a.R = 128;
+  a.G = 1;
+  a.out = out;
+  a.ldo = ldo;
+  a.bias = bias;
+  a.scale = scale;
+  a.A = A;
+  a.lda = K;
+  return a;
+}
+
+#define RC(x)              \
+  do {                     \
+    int _rc = (x);         \
+    if (_rc) return _rc;   \
+  } while (0)
+#define KLAUNCH()                                                                                       \
+  do {                                                                                                  \
+    e->launches++;                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess) return fail(TONE_ECUDA, "launch at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int run_norm(tone_engine* e, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
+                    bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
+  NormArgs a{r, g1, g2, n, M, kv, e->d_slots, rows_per_stream, kv_row_off};
+  norm_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
+  KLAUNCH();
+  return 0;
+}
+
+static int run_ff(tone_engine* e, cudaStream_t st, int M, float* r, const WeightMat& up, const float* up_b,
+                  const WeightMat& down, const float* down_b) {
+  const int mt = (M + 127) / 128;
+  GemmArgs a = dense_args(M, D_MODEL, e->n, e->h, D_FF, up_b, 1.f);
+  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, e->m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+  GemmArgs b = dense_args(M, D_FF, e->h, r, D_MODEL, down_b, 0.5f);
+  RC((gemm<G_RESID, BN_RESID>(e, st, e->m_h, down, b, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+  return 0;
+}
+
+// taps: optional host pointer [17][B*T][384]; when set the step synchronises after every layer (debug only)
+static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
+  const int T = e->T, T2 = e->T2, F = e->F, C = e->C;
+  e->launches = 0;
+  auto tap = [&](int idx, const float* src, int rows) -> int {
+    if (!taps) return 0;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(taps + (size_t)idx * B * T * D_MODEL, src, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  {
+    BeginArgs a;
+    memset(&a, 0, sizeof(a));
+    a.slots = e->d_slots;
+    a.pcm = e->d_pcm;
+    a.pre = e->st_pre;
+    a.feat = e->st_feat;
+    a.x1 = e->st_x1;
+    a.kv14 = e->st_kv14;
+    a.kv15 = e->st_kv15;
+    a.mhsa_len = e->st_len;
+    a.len_in = e->d_len_in;
+    a.basis = e->basis;
+    a.mel_start = e->mel_start;
+    a.mel_bin = e->mel_bin;
+    a.mel_w = e->mel_w;
+    a.pre_norm_g = e->pre_norm_g;
+    a.C = C;
+    a.F = F;
+    a.T = T;
+    a.T2 = T2;
+    const size_t smem = (size_t)(C + HOP + F * 162 + F * N_MELS) * 4;
+    begin_step_kernel<<<B, BEGIN_THREADS, smem, st>>>(a);
+    KLAUNCH();
+  }
+  {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = B;
+    a.nk = 11;
+    a.R = F;
+    a.G = 128 / F;
+    a.slots = e->d_slots;
+    a.out = e->st_x1;
+    a.ldo = X1_ROW;
+    a.alpha = e->conv0_alpha;
+    a.beta = e->conv0_beta;
+    a.out_slot_stride = (long long)X1_ROWS_MAX * X1_ROW;
+    a.out_row_off = SUB2_ROWS;
+    a.A = e->st_feat;
+    a.a_slot_stride = FEAT_ROWS_MAX * N_MELS;
+    RC((gemm<G_CONV0, BN_CONV>(e, st, e->m_feat, e->conv0_w, a, (B + a.G - 1) / a.G, X1_ROW / BN_CONV, B * F, X1_ROW)));
+  }
+  {  // conv1: rows = T frames per stream, K = 11 kernel rows x (12 positions x 32 channels), N = 2 positions x 64 ch
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = B;
+    a.nk = 66;
+    a.R = T;
+    a.G = 128 / T;
+    a.slots = e->d_slots;
+    a.out = e->c1;
+    a.ldo = SUB_OUT;
+    a.alpha = e->conv1_alpha;
+    a.beta = e->conv1_beta;
+    a.A = e->st_x1;
+    a.a_slot_stride = (long long)X1_ROWS_MAX * X1_ROW;
+    RC((gemm<G_CONV1, BN_CONV>(e, st, e->m_x1, e->conv1_w, a, (B + a.G - 1) / a.G, SUB_OUT / BN_CONV, B * T, SUB_OUT)));
+  }
+  int M = B * T;
+  {
+    GemmArgs a = dense_args(M, SUB_OUT, e->c1, e->r_full, D_MODEL, nullptr, 1.f);
+    RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / BN_STORE, M, D_MODEL)));
+  }
+  RC(run_norm(e, st, e->r_full, e->out_norm_g, e->L[0].n_ff1, e->n, M));
+  RC(tap(0, e->r_full, M));
+
+  for (int l = 0; l < N_LAYERS; ++l) {
+    LayerW& L = e->L[l];
+    const bool reduced = l > 6 && l <= 14;
+    const int Tl = reduced ? T2 : T;
+    float* r = reduced ? e->r_red : e->r_full;
+    M = B * Tl;
+    const int mt = (M + 127) / 128;
+    RC(run_ff(e, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b));
+    // ---- attention
+    AttnArgs at;
+    memset(&at, 0, sizeof(at));
+    at.P = e->P;
+    at.ctx = e->ctx;
+    at.rope_cos = e->rope_cos;
+    at.rope_sin = e->rope_sin;
+    at.len_in = e->d_len_in;
+    at.T = Tl;
+    at.recompute = RECOMPUTE[l] ? 1 : 0;
+    if (l < 14) {
+      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M));
+      at.S = 0;
+      at.Tk = Tl;
+      if (RECOMPUTE[l]) {
+        GemmArgs a = dense_args(M, D_MODEL, e->n, e->qkv, 3 * D_MODEL, L.qkv_b, 1.f);
+        RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
+        at.q = e->qkv;
+        at.k = e->qkv + D_MODEL;
+        at.v = e->qkv + 2 * D_MODEL;
+        at.ldq = at.ldk = at.ldv = 3 * D_MODEL;
+        at.q_ln_w = L.qln_w;
+        at.q_ln_b = L.qln_b;
+        at.k_ln_w = L.kln_w;
+        at.k_ln_b = L.kln_b;
+      } else {
+        GemmArgs a = dense_args(M, D_MODEL, e->n, e->qkv, D_MODEL, L.qkv_b, 1.f);
+        RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.qkv, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+        at.v = e->qkv;
+        at.ldv = D_MODEL;
+      }
+    } else {
+      const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
+      bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
+      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, kvbuf, Tl, S));
+      float* qbuf = e->qkv;
+      float* kvout = e->qkv + (size_t)e->rows_alloc * D_MODEL;
+      GemmArgs a = dense_args(M, D_MODEL, e->n, qbuf, D_MODEL, L.q_b, 1.f);
+      RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.q, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+      GemmArgs k;
+      memset(&k, 0, sizeof(k));
+      k.M = B;
+      k.nk = D_MODEL / 64;
+      k.R = S + Tl;
+      k.G = 128 / k.R;
+      k.slots = e->d_slots;
+      k.out = kvout;
+      k.ldo = 2 * D_MODEL;
+      k.bias = L.kv_b;
+      k.A = kvbuf;
+      k.lda = D_MODEL;
+      k.a_slot_stride = KV_ROWS_MAX * D_MODEL;
+      RC((gemm<G_KV, BN_KV>(e, st, l == 14 ? e->m_kv14 : e->m_kv15, L.kv, k, (B + k.G - 1) / k.G, 2 * D_MODEL / BN_KV,
+                            B * k.R, 2 * D_MODEL)));
+      at.S = S;
+      at.Tk = S + Tl;
+      at.q = qbuf;
+      at.ldq = D_MODEL;
+      at.k = kvout;
+      at.v = kvout + D_MODEL;
+      at.ldk = at.ldv = 2 * D_MODEL;
+      at.q_ln_w = L.qln_w;
+      at.q_ln_b = L.qln_b;
+      at.k_ln_w = L.kln_w;
+      at.k_ln_b = L.kln_b;
+      at.mask_mode = (l == 14) ? 2 : 1;
+    }
+    attention_kernel<<<B * N_HEADS, 64, 0, st>>>(at);
+    KLAUNCH();
+    {
+      GemmArgs a = dense_args(M, D_MODEL, e->ctx, r, D_MODEL, L.wo_b, 1.f);
+      RC((gemm<G_RESID, BN_RESID>(e, st, e->m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+    }
+    // ---- convolution module
+    RC(run_norm(e, st, r, nullptr, L.n_conv, e->n, M));
+    {
+      GemmArgs a = dense_args(M, D_MODEL, e->n, e->g, D_MODEL, L.pw1_b, 1.f);
+      RC((gemm<G_GLU, BN_GLU>(e, st, e->m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+    }
+    {
+      DwArgs d;
+      d.g = e->g;
+      d.cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;
+      d.cache_slot_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
+      d.slots = e->d_slots;
+      d.w = L.dw_w;
+      d.bias = L.dw_b;
+      d.e = e->ebuf;
+      d.T = Tl;
+      dwconv_kernel<<<dim3(B, 2), 96, 0, st>>>(d);
+      KLAUNCH();
+    }
+    {
+      GemmArgs a = dense_args(M, D_MODEL, e->ebuf, r, D_MODEL, L.pw2_b, 1.f);
+      RC((gemm<G_RESID, BN_RESID>(e, st, e->m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+    }
+    // ---- second feed-forward, norm_out and what follows the layer
+    RC(run_norm(e, st, r, nullptr, L.n_ff2, e->n, M));
+    RC(run_ff(e, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b));
+    if (l == 6) {
+      RC(run_norm(e, st, r, L.n_out, nullptr, nullptr, M));   // r_full = layer output = residual kept for layer 14
+      RedArgs ra{e->r_full, e->st_red, e->d_slots, e->red_dw_w, e->red_dw_b, e->m_red, T, T2};
+      reduction_dw_kernel<<<B, D_MODEL, 0, st>>>(ra);
+      KLAUNCH();
+      const int M2 = B * T2;
+      GemmArgs a = dense_args(M2, D_FF, e->m_red, e->r_red, D_MODEL, e->red_pw_b, 1.f);
+      RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
+      RC(run_norm(e, st, e->r_red, nullptr, e->L[7].n_ff1, e->n, M2));
+      RC(tap(1 + l, e->r_red, M2));
+    } else if (l == 14) {
+      UpsampleArgs ua{e->r_full, e->r_red, L.n_out, e->L[15].n_ff1, e->n, B, T, T2};
+      upsample_norm_kernel<<<(B * T + 7) / 8, 256, 0, st>>>(ua);
+      KLAUNCH();
+      RC(tap(1 + l, e->r_full, B * T));
+    } else if (l == 15) {
+      RC(run_norm(e, st, r, L.n_out, nullptr, e->n, M));
+      RC(tap(1 + l, r, M));
+    } else {
+      RC(run_norm(e, st, r, L.n_out, e->L[l + 1].n_ff1, e->n, M));
+      RC(tap(1 + l, r, M));
+    }
+  }
+  {
+    M = B * T;
+    GemmArgs a = dense_args(M, D_MODEL, e->n, e->logprobs, N_CLASSES, e->dec_b, 1.f);
+    a.tokens = e->d_tokens;
+    RC((gemm<G_DECODER, DEC_PAD>(e, st, e->m_n, e->dec_w, a, (M + 127) / 128, 1, M, N_CLASSES)));
+  }
+  e->launches_per_step = e->launches;
+  return 0;
+}
+
+static int check_step_args(tone_engine* e, int B) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  if (!e->finalized) return fail(TONE_ESTATE, "weights not finalized");
+  if (B < 1 || B > e->cfg.max_batch) return fail(TONE_EINVAL, "batch %d outside [1, %d]", B, e->cfg.max_batch);
+  return 0;
+}
+
+static int launch_step(tone_engine* e, int B, cudaStream_t st) {
+  if (!e->cfg.use_graph) return run_step(e, B, st, nullptr);
+  auto it = e->graphs.find(B);
+  if (it == e->graphs.end()) {
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_step(e, B, e->stream, nullptr);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(TONE_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    it = e->graphs.emplace(B, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, st));
+  return 0;
+}
+
+extern "C" int tone_stage(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm) {
+  RC(check_step_args(e, B));
+  if (!slots || !pcm) return fail(TONE_EINVAL, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < B; ++i)
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
+      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
+  if (slots != e->p_slots) memcpy(e->p_slots, slots, (size_t)B * 4);
+  if (pcm != e->p_pcm) memcpy(e->p_pcm, pcm, (size_t)B * e->C * 4);
+  CK(cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_pcm, e->p_pcm, (size_t)B * e->C * 4, cudaMemcpyHostToDevice, e->stream));
+  return TONE_OK;
+}
+
+extern "C" int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream) {
+  RC(check_step_args(e, B));
+  CK(cudaSetDevice(e->cfg.device));
+  return launch_step(e, B, cuda_stream ? (cudaStream_t)cuda_stream : e->stream);
+}
+
+extern "C" int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens) {
+  RC(check_step_args(e, B));
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t nl = (size_t)B * e->T * N_CLASSES * 4, nt = (size_t)B * e->T * 4;
+  if (logprobs) CK(cudaMemcpyAsync(e->p_logprobs, e->logprobs, nl, cudaMemcpyDeviceToHost, e->stream));
+  if (tokens) CK(cudaMemcpyAsync(e->p_tokens, e->d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (logprobs && logprobs != e->p_logprobs) memcpy(logprobs, e->p_logprobs, nl);
+  if (tokens && tokens != e->p_tokens) memcpy(tokens, e->p_tokens, nt);
+  return TONE_OK;
+}
+
+extern "C" int tone_sync(tone_engine* e) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  return TONE_OK;
+}
+
+extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
+                         int32_t* tokens) {
+  RC(tone_stage(e, B, slots, pcm));
+  RC(launch_step(e, B, e->stream));
+  return tone_fetch(e, B, logprobs, tokens);
+}
+
+extern "C" int tone_step_debug(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
+                               int32_t* tokens, float* taps) {
+  RC(tone_stage(e, B, slots, pcm));
+  RC(run_step(e, B, e->stream, taps));
+  return tone_fetch(e, B, logprobs, tokens);
+}
+
+// Pinned staging buffers of the engine: writing inputs / reading outputs there skips one host copy per step.
+extern "C" int tone_host_buffers(tone_engine* e, int32_t** slots, int32_t** pcm, float** logprobs, int32_t** tokens) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  if (slots) *slots = e->p_slots;
+  if (pcm) *pcm = e->p_pcm;
+  if (logprobs) *logprobs = e->p_logprobs;
+  if (tokens) *tokens = e->p_tokens;
+  return TONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ state wire format
+// Flat fp16 order (tone/nn/model.py:259-267): preproc 80 | mhsa (2,30,384) | conv (16,384,30) | len 1 |
+// sub1 (1,10,64) | sub2 (32,8,44) | reduction (384,1).
+namespace {
+struct Off {
+  static const int pre = 0, mhsa = 80, conv = mhsa + 2 * 30 * 384, len = conv + 16 * 384 * 30, sub1 = len + 1,
+                   sub2 = sub1 + 640, red = sub2 + 32 * 8 * 44, end = red + 384;
+};
+static_assert(Off::end == TONE_STATE_SIZE, "state layout");
+}  // namespace
+
+extern "C" int tone_export_state(tone_engine* e, int32_t slot, uint16_t* out) {
+  if (!e || !out) return fail(TONE_EINVAL, "null argument");
+  if (slot < 0 || slot >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slot);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t s = slot;
+  const int F = e->F, T = e->T, T2 = e->T2;
+  std::vector<uint16_t> pre(HOP), feat(SUB1_ROWS * N_MELS), x1((size_t)SUB2_ROWS * X1_ROW), k14(15 * D_MODEL),
+      k15(30 * D_MODEL), conv((size_t)N_LAYERS * CONV_S * D_MODEL);
+  std::vector<float> red(D_MODEL);
+  int len = 0;
+  CK(cudaMemcpy(pre.data(), e->st_pre + s * HOP, HOP * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(feat.data(), e->st_feat + (s * FEAT_ROWS_MAX + F) * N_MELS, feat.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(x1.data(), e->st_x1 + (s * X1_ROWS_MAX + F) * X1_ROW, x1.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(k14.data(), e->st_kv14 + (s * KV_ROWS_MAX + T2) * D_MODEL, k14.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(k15.data(), e->st_kv15 + (s * KV_ROWS_MAX + T) * D_MODEL, k15.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(conv.data(), e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, conv.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(red.data(), e->st_red + s * D_MODEL, D_MODEL * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&len, e->st_len + s, 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < HOP; ++i) out[Off::pre + i] = pre[i];
+  for (int r = 0; r < 30; ++r)
+    for (int c = 0; c < D_MODEL; ++c) {
+      out[Off::mhsa + r * D_MODEL + c] = r < 15 ? 0 : f2h(bf2f(k14[(size_t)(r - 15) * D_MODEL + c]));
+      out[Off::mhsa + (30 + r) * D_MODEL + c] = f2h(bf2f(k15[(size_t)r * D_MODEL + c]));
+    }
+  for (int l = 0; l < N_LAYERS; ++l)
+    for (int c = 0; c < D_MODEL; ++c)
+      for (int t = 0; t < CONV_S; ++t)
+        out[Off::conv + ((size_t)l * D_MODEL + c) * CONV_S + t] = f2h(bf2f(conv[((size_t)l * CONV_S + t) * D_MODEL + c]));
+  out[Off::len] = f2h((float)len);
+  for (int i = 0; i < SUB1_ROWS * N_MELS; ++i) out[Off::sub1 + i] = f2h(bf2f(feat[i]));
+  for (int c = 0; c < 32; ++c)
+    for (int r = 0; r < SUB2_ROWS; ++r)
+      for (int f = 0; f < 44; ++f)
+        out[Off::sub2 + (c * SUB2_ROWS + r) * 44 + f] = f2h(bf2f(x1[(size_t)r * X1_ROW + f * 32 + c]));
+  for (int c = 0; c < D_MODEL; ++c) out[Off::red + c] = f2h(red[c]);
+  return TONE_OK;
+}
+
+extern "C" int tone_import_state(tone_engine* e, int32_t slot, const uint16_t* in) {
+  if (!e || !in) return fail(TONE_EINVAL, "null argument");
+  if (slot < 0 || slot >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slot);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t s = slot;
+  const int F = e->F, T = e->T, T2 = e->T2;
+  std::vector<uint16_t> pre(HOP), feat(SUB1_ROWS * N_MELS), x1((size_t)SUB2_ROWS * X1_ROW), k14(15 * D_MODEL),
+      k15(30 * D_MODEL), conv((size_t)N_LAYERS * CONV_S * D_MODEL);
+  std::vector<float> red(D_MODEL);
+  for (int i = 0; i < HOP; ++i) pre[i] = in[Off::pre + i];
+  for (int r = 0; r < 30; ++r)
+    for (int c = 0; c < D_MODEL; ++c) {
+      if (r >= 15) k14[(size_t)(r - 15) * D_MODEL + c] = f2bf(h2f(in[Off::mhsa + r * D_MODEL + c]));
+      k15[(size_t)r * D_MODEL + c] = f2bf(h2f(in[Off::mhsa + (30 + r) * D_MODEL + c]));
+    }
+  for (int l = 0; l < N_LAYERS; ++l)
+    for (int c = 0; c < D_MODEL; ++c)
+      for (int t = 0; t < CONV_S; ++t)
+        conv[((size_t)l * CONV_S + t) * D_MODEL + c] = f2bf(h2f(in[Off::conv + ((size_t)l * D_MODEL + c) * CONV_S + t]));
+  int len = (int)lrintf(h2f(in[Off::len]));
+  len = std::max(0, std::min(len, MHSA_S));
+  for (int i = 0; i < SUB1_ROWS * N_MELS; ++i) feat[i] = f2bf(h2f(in[Off::sub1 + i]));
+  for (int c = 0; c < 32; ++c)
+    for (int r = 0; r < SUB2_ROWS; ++r)
+      for (int f = 0; f < 44; ++f)
+        x1[(size_t)r * X1_ROW + f * 32 + c] = f2bf(h2f(in[Off::sub2 + (c * SUB2_ROWS + r) * 44 + f]));
+  for (int c = 0; c < D_MODEL; ++c) red[c] = h2f(in[Off::red + c]);
+  CK(cudaMemcpy(e->st_pre + s * HOP, pre.data(), HOP * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_feat + (s * FEAT_ROWS_MAX + F) * N_MELS, feat.data(), feat.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_x1 + (s * X1_ROWS_MAX + F) * X1_ROW, x1.data(), x1.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_kv14 + (s * KV_ROWS_MAX + T2) * D_MODEL, k14.data(), k14.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_kv15 + (s * KV_ROWS_MAX + T) * D_MODEL, k15.data(), k15.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, conv.data(), conv.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_red + s * D_MODEL, red.data(), D_MODEL * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->st_len + s, &len, 4, cudaMemcpyHostToDevice));
+  return TONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM self-test
+template <int BN>
+static int selftest_bn(tone_engine* e, int M, int N, int K, const bf16* dA, const bf16* dW, float* dC) {
+  CUtensorMap ma, mw;
+  RC(make_map_2d(e, &ma, (void*)dA, M, K, 128, false));
+  RC(make_map_2d(e, &mw, (void*)dW, N, K, BN, true));
+  GemmArgs a = dense_args(M, K, dA, dC, N, nullptr, 1.f);
+  a.W = dW;
+  a.ldw = K;
+  cudaError_t err = launch_gemm_tc<G_STORE_F32, BN>(e->stream, ma, mw, a, (M + 127) / 128, N / BN);
+  if (err != cudaSuccess) return fail(TONE_ECUDA, "selftest launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+extern "C" int tone_selftest_gemm(tone_engine* e, int32_t M, int32_t N, int32_t K, const float* A, const float* Wm,
+                                  float* Cout, int32_t block_n) {
+  if (!e || !A || !Wm || !Cout) return fail(TONE_EINVAL, "null argument");
+  if (K % 64 || N % block_n || M < 1) return fail(TONE_EINVAL, "need K %% 64 == 0 and N %% block_n == 0");
+  CK(cudaSetDevice(e->cfg.device));
+  std::vector<uint16_t> a((size_t)M * K), w((size_t)N * K);
+  for (size_t i = 0; i < a.size(); ++i) a[i] = f2bf(A[i]);
+  for (size_t i = 0; i < w.size(); ++i) w[i] = f2bf(Wm[i]);
+  bf16 *dA = nullptr, *dW = nullptr;
+  float* dC = nullptr;
+  const size_t Mp = ((size_t)M + 127) / 128 * 128;
+  CK(cudaMalloc((void**)&dA, Mp * K * 2));
+  CK(cudaMemset(dA, 0, Mp * K * 2));
+  CK(cudaMalloc((void**)&dW, w.size() * 2));
+  CK(cudaMalloc((void**)&dC, (size_t)M * N * 4));
+  CK(cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+  int rc;
+  if (block_n == 32) rc = selftest_bn<32>(e, M, N, K, dA, dW, dC);
+  else if (block_n == 64) rc = selftest_bn<64>(e, M, N, K, dA, dW, dC);
+  else if (block_n == 128) rc = selftest_bn<128>(e, M, N, K, dA, dW, dC);
+  else rc = fail(TONE_EINVAL, "block_n must be 32, 64 or 128");
+  if (!rc) {
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    if (se != cudaSuccess) rc = fail(TONE_ECUDA, "selftest run: %s", cudaGetErrorString(se));
+  }
+  if (!rc) {
+    cudaError_t ce = cudaMemcpy(Cout, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) rc = fail(TONE_ECUDA, "selftest copy: %s", cudaGetErrorString(ce));
+  }
+  cudaFree(dA);
+  cudaFree(dW);
+  cudaFree(dC);
+  return rc;
+}

@@ -1,0 +1,328 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[128 x BN] (fp32, TMEM) = A[128 x K] * W[BN x K]^T, bf16 operands.
+//
+// One output tile per CTA, 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM owner and
+// tcgen05.mma issuer (one lane), warps 2..5 = epilogue (one TMEM lane quarter each).  Operand tiles are
+// K-major rows of 64 bf16 (128 B) in the 128-byte swizzle, staged through a STAGES-deep mbarrier ring.
+//
+// The A tile is either 128 consecutive rows of a dense [M][K] activation matrix, or a GATHER of G boxes of R
+// rows, one box per stream, addressed by slot id through a 3-D tensor map over the per-stream state pool.  The
+// gather form is how the conv-subsampling layers run as implicit GEMMs without materialising im2col, and how the
+// cached-context K/V projections read [cache | new rows] in place.
+#pragma once
+
+#include "common.cuh"
+
+namespace tone {
+
+enum GemmKind : int {
+  G_STORE_F32 = 0,  // out fp32 = acc + bias                                 (q/k/v, out-linear, reduction pw)
+  G_RESID = 1,      // r fp32 += scale * (acc + bias)                        (ff down, attn out, conv pw2)
+  G_SWIGLU = 2,     // h bf16 = silu(acc_g + b_g) * (acc_v + b_v)            (ff up; tile = 64 gate | 64 value cols)
+  G_GLU = 3,        // g bf16 = (acc_a + b_a) * sigmoid(acc_b + b_b)         (conv pw1; tile = 32 a | 32 b cols)
+  G_CONV0 = 4,      // x1[slot] bf16 = silu(acc*alpha + beta)                (gather A from feature rows)
+  G_CONV1 = 5,      // c1 bf16 = silu(acc*alpha + beta)                      (gather A from x1 windows)
+  G_KV = 6,         // out fp32 = acc + bias, gather A from [cache|new] rows (layers 14, 15)
+  G_DECODER = 7,    // logprobs = log_softmax(acc + bias)[0:35], argmax      (BN = 48)
+};
+
+struct GemmArgs {
+  int M;            // dense: valid rows; gather: number of streams in the batch
+  int nk;           // K iterations of 64
+  int R, G;         // gather: rows per stream box, boxes per 128-row tile
+  const int* slots; // gather: slot id per batch position
+  void* out;        // output base
+  int ldo;          // output leading dimension (elements)
+  const float* bias;
+  const float* alpha;
+  const float* beta;
+  float scale;
+  long long out_slot_stride;  // G_CONV0: elements between consecutive slots of x1
+  int out_row_off;            // G_CONV0: first row written inside a slot (the cached rows come first)
+  int* tokens;                // G_DECODER
+  // Raw operand views, used only by the SIMT debug kernels (gemm_ref.cuh); the tensor-core path reads through
+  // the tensor maps.
+  const bf16* A;
+  int lda;
+  long long a_slot_stride;    // gather: elements between consecutive slots of the A pool
+  const bf16* W;
+  int ldw;
+};
+
+template <int KIND>
+struct KindTraits {
+  static constexpr bool gather = (KIND == G_CONV0 || KIND == G_CONV1 || KIND == G_KV);
+};
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = (BN > 64) ? 3 : 4;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;  // + barriers + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------- epilogues
+// Row bookkeeping shared by all kinds.
+struct RowInfo {
+  bool valid;
+  long long out_row;  // row index into a dense output, or element offset base for the scatter kind
+};
+
+template <int KIND>
+__device__ __forceinline__ RowInfo row_info(const GemmArgs& a, int row_in_tile) {
+  RowInfo ri;
+  if constexpr (KindTraits<KIND>::gather) {
+    int g = row_in_tile / a.R;
+    int j = row_in_tile - g * a.R;
+    int b = blockIdx.x * a.G + g;
+    ri.valid = (g < a.G) && (b < a.M);
+    if constexpr (KIND == G_CONV0) {
+      int slot = ri.valid ? a.slots[b] : 0;
+      ri.out_row = (long long)slot * a.out_slot_stride + (long long)(a.out_row_off + j) * a.ldo;
+    } else {
+      ri.out_row = (long long)b * a.R + j;
+    }
+  } else {
+    int m = blockIdx.x * 128 + row_in_tile;
+    ri.valid = m < a.M;
+    ri.out_row = m;
+  }
+  return ri;
+}
+
+template <int KIND, int BN>
+__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int row_in_tile) {
+  const RowInfo ri = row_info<KIND>(a, row_in_tile);
+  const int n0 = blockIdx.y * BN;
+  float v[16];
+  if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
+    float* out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      tmem_ld16(tmem_row_base + c, v);
+      if (ri.valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 o;
+          o.x = v[i + 0] + (a.bias ? a.bias[n0 + c + i + 0] : 0.f);
+          o.y = v[i + 1] + (a.bias ? a.bias[n0 + c + i + 1] : 0.f);
+          o.z = v[i + 2] + (a.bias ? a.bias[n0 + c + i + 2] : 0.f);
+          o.w = v[i + 3] + (a.bias ? a.bias[n0 + c + i + 3] : 0.f);
+          *reinterpret_cast<float4*>(out + c + i) = o;
+        }
+      }
+    }
+  } else if constexpr (KIND == G_RESID) {
+    float* out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      tmem_ld16(tmem_row_base + c, v);
+      if (ri.valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 o = *reinterpret_cast<float4*>(out + c + i);
+          o.x += a.scale * (v[i + 0] + a.bias[n0 + c + i + 0]);
+          o.y += a.scale * (v[i + 1] + a.bias[n0 + c + i + 1]);
+          o.z += a.scale * (v[i + 2] + a.bias[n0 + c + i + 2]);
+          o.w += a.scale * (v[i + 3] + a.bias[n0 + c + i + 3]);
+          *reinterpret_cast<float4*>(out + c + i) = o;
+        }
+      }
+    }
+  } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
+    constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
+    bf16* out = reinterpret_cast<bf16*>(a.out) + ri.out_row * a.ldo + blockIdx.y * HW;
+    float w[16];
+#pragma unroll 1
+    for (int c = 0; c < HW; c += 16) {
+      tmem_ld16(tmem_row_base + c, v);
+      tmem_ld16(tmem_row_base + HW + c, w);
+      if (ri.valid) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float x0 = v[i] + a.bias[n0 + c + i], x1 = v[i + 1] + a.bias[n0 + c + i + 1];
+          float y0 = w[i] + a.bias[n0 + HW + c + i], y1 = w[i + 1] + a.bias[n0 + HW + c + i + 1];
+          float r0, r1;
+          if constexpr (KIND == G_SWIGLU) {
+            r0 = silu_f(x0) * y0;
+            r1 = silu_f(x1) * y1;
+          } else {
+            r0 = x0 * sigmoid_f(y0);
+            r1 = x1 * sigmoid_f(y1);
+          }
+          p[i / 2] = pack_bf16x2(r0, r1);
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + c);
+        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+    }
+  } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
+    // channel index of column n: conv0 n = f*32 + o (o = n % 32); conv1 tile column c = j*64 + o (o = c % 64)
+    constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
+    bf16* out = reinterpret_cast<bf16*>(a.out) +
+                (KIND == G_CONV0 ? ri.out_row : ri.out_row * (long long)a.ldo) + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      tmem_ld16(tmem_row_base + c, v);
+      if (ri.valid) {
+        uint32_t p[8];
+        const int ch0 = (n0 + c) % CH;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float r0 = silu_f(v[i] * a.alpha[ch0 + i] + a.beta[ch0 + i]);
+          float r1 = silu_f(v[i + 1] * a.alpha[ch0 + i + 1] + a.beta[ch0 + i + 1]);
+          p[i / 2] = pack_bf16x2(r0, r1);
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + c);
+        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+    }
+  } else if constexpr (KIND == G_DECODER) {
+    static_assert(KIND != G_DECODER || BN == 48, "decoder tile is 48 columns (35 classes + padding)");
+    float lg[48];
+    tmem_ld16(tmem_row_base + 0, lg);
+    tmem_ld16(tmem_row_base + 16, lg + 16);
+    tmem_ld16(tmem_row_base + 32, lg + 32);
+    if (ri.valid) {
+      float mx = -INFINITY;
+      int am = 0;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) {
+        lg[i] += a.bias[i];
+        if (lg[i] > mx) {  // strict > keeps the first maximum (numpy argmax, tone/decoder.py:57)
+          mx = lg[i];
+          am = i;
+        }
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) s += expf(lg[i] - mx);
+      const float lse = mx + logf(s);
+      float* out = reinterpret_cast<float*>(a.out) + ri.out_row * 35;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
+      if (a.tokens) a.tokens[ri.out_row] = am;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int KIND, int BN>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      int nvalid = 1;
+      if constexpr (KindTraits<KIND>::gather) {
+        nvalid = a.M - blockIdx.x * a.G;
+        nvalid = nvalid > a.G ? a.G : nvalid;
+      }
+      const uint32_t a_bytes = KindTraits<KIND>::gather ? (uint32_t)(nvalid * a.R * 128) : (uint32_t)Cfg::A_BYTES;
+      for (int it = 0; it < a.nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
+        uint8_t* dA = sA + s * Cfg::A_BYTES;
+        if constexpr (KIND == G_CONV0) {
+          // K iteration = kernel row kt; box = 64 mel bins x R frames starting at feature row kt
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], 0, it, a.slots[blockIdx.x * a.G + g]);
+        } else if constexpr (KIND == G_CONV1) {
+          // K iteration = (kt, 64-wide piece kc of the 12-position x 32-channel window at f0 = 2*blockIdx.y).
+          // x1 is viewed as [slot][row triple][row in triple][44*32]; output frame t reads row 3t + kt, so the
+          // box walks R consecutive triples starting at kt/3 with the in-triple row fixed to kt%3.
+          const int kt = it / 6, kc = it - kt * 6;
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_4d(dA + g * a.R * 128, &tmA, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3,
+                        a.slots[blockIdx.x * a.G + g]);
+        } else if constexpr (KIND == G_KV) {
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
+        } else {
+          tma_load_2d(dA, &tmA, &full[s], it * 64, blockIdx.x * 128);
+        }
+        tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], it * 64, (KIND == G_CONV1) ? 0 : blockIdx.y * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BN);
+      for (int it = 0; it < a.nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t da = make_sw128_desc(smem_u32(sA + s * Cfg::A_BYTES));
+        const uint64_t db = make_sw128_desc(smem_u32(sB + s * Cfg::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle atom
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);        // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q * 32 + lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// Must be called once per instantiation (outside stream capture) before the first launch.
+template <int KIND, int BN>
+inline cudaError_t configure_gemm_tc() {
+  return cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TileCfg<BN>::SMEM_BYTES);
+}
+
+template <int KIND, int BN>
+inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                                  const GemmArgs& a, int m_tiles, int n_tiles) {
+  using Cfg = TileCfg<BN>;
+  gemm_tc_kernel<KIND, BN><<<dim3(m_tiles, n_tiles), 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
+  return cudaGetLastError();
+}
+
+}  // namespace tone

@@ -1,0 +1,494 @@
+// Bandwidth-class kernels of the streaming step (everything that is not a GEMM):
+//   begin_step_kernel   PCM -> log-mel -> RMSNorm(64) rows, plus the start-of-step cache rolls       (A1, K1-K3, K13, K21)
+//   norm_kernel         RMSNorm(384) variants feeding the GEMMs, optional cache-row scatter          (A3, K7, K13)
+//   attention_kernel    per-head LayerNorm + RoPE + scores + masked softmax + P.V, score sharing     (A5, K11)
+//   dwconv_kernel       causal depthwise conv k=31 + BN + SiLU with its 30-frame cache               (A4.3, K15)
+//   reduction_dw_kernel / upsample_norm_kernel                                                       (K17, K18)
+// Section/kernel numbers refer to SURVEY.md Appendix A and §2b.
+#pragma once
+
+#include "common.cuh"
+
+namespace tone {
+
+constexpr int D_MODEL = 384;
+constexpr int N_HEADS = 8;
+constexpr int D_HEAD = 48;
+constexpr int N_MELS = 64;
+constexpr int N_BINS = 81;
+constexpr int WIN = 160;
+constexpr int HOP = 80;
+constexpr int MHSA_S = 30;
+constexpr int CONV_S = 30;
+constexpr int SUB1_ROWS = 10;
+constexpr int SUB2_ROWS = 8;
+constexpr int X1_ROW = 44 * 32;      // elements per conv0-output time row (f-major, channel-minor)
+constexpr int FEAT_ROWS_MAX = 50;    // 10 cached + up to 40 new feature rows per slot
+constexpr int X1_ROWS_MAX = 48;      // 8 cached + up to 40 new rows per slot
+constexpr int KV_ROWS_MAX = 44;      // 30 cached + up to 13 new rows (+1 pad) per stateful layer
+constexpr int MAX_FRAMES = 40;       // 400 ms
+constexpr int MAX_T = 13;
+
+// ------------------------------------------------------------------------------------------------ begin step
+struct BeginArgs {
+  const int* slots;          // [B]
+  const int* pcm;            // [B][C] int32
+  __half* pre;               // [slots][80] last samples of the previous chunk (fp16-exact values)
+  bf16* feat;                // [slots][FEAT_ROWS_MAX][64]
+  bf16* x1;                  // [slots][X1_ROWS_MAX][X1_ROW]
+  bf16* kv14;                // [slots][KV_ROWS_MAX][384]   layer-14 [cache | new] rows (15 + T2)
+  bf16* kv15;                // [slots][KV_ROWS_MAX][384]   layer-15 [cache | new] rows (30 + T)
+  int* mhsa_len;             // [slots]
+  int* len_in;               // [B] length seen by this step's masks (value entering the step)
+  const float* basis;        // [160][162] pre-emphasis * Hann * DFT, column k = cos bin k / -sin bin k-81
+  const float* hann_unused;
+  const int* mel_start;      // [65] CSR over mel filters
+  const unsigned char* mel_bin;  // [nnz]
+  const float* mel_w;        // [nnz]
+  const float* pre_norm_g;   // [64]
+  int C, F, T, T2;
+};
+
+// One CTA per stream.  352 threads: threads [0,162) accumulate DFT column k for the first half of the frames,
+// threads [162,324) the same columns for the second half.
+constexpr int BEGIN_THREADS = 352;
+
+__global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginArgs a) {
+  extern __shared__ float sm[];
+  const int F = a.F, C = a.C;
+  float* u = sm;                          // [C + 80]
+  float* spec = u + (C + 80);             // [F][162]
+  float* featS = spec + F * 162;          // [F][64]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int slot = a.slots[b];
+
+  // ---- start-of-step cache rolls: the last rows of [cache | previous new rows] become the cache
+  {
+    // feature rows [F, F+10) -> [0, 10)  (80 x 16 B), x1 rows [F, F+8) -> [0, 8) (1408 x 16 B): disjoint ranges
+    uint4* f4 = reinterpret_cast<uint4*>(a.feat + (size_t)slot * FEAT_ROWS_MAX * N_MELS);
+    if (tid < SUB1_ROWS * N_MELS / 8) f4[tid] = f4[F * N_MELS / 8 + tid];
+    uint4* x4 = reinterpret_cast<uint4*>(a.x1 + (size_t)slot * X1_ROWS_MAX * X1_ROW);
+    for (int i = tid; i < SUB2_ROWS * X1_ROW / 8; i += BEGIN_THREADS) x4[i] = x4[F * X1_ROW / 8 + i];
+    // attention caches overlap their source: load everything, barrier, store
+    uint4* k15 = reinterpret_cast<uint4*>(a.kv15 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
+    uint4* k14 = reinterpret_cast<uint4*>(a.kv14 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
+    constexpr int RV = D_MODEL / 8;       // uint4 per row
+    uint4 r15[5], r14[3];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int idx = tid + i * BEGIN_THREADS;
+      if (idx < MHSA_S * RV) r15[i] = k15[a.T * RV + idx];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      int idx = tid + i * BEGIN_THREADS;
+      if (idx < (MHSA_S / 2) * RV) r14[i] = k14[a.T2 * RV + idx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int idx = tid + i * BEGIN_THREADS;
+      if (idx < MHSA_S * RV) k15[idx] = r15[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      int idx = tid + i * BEGIN_THREADS;
+      if (idx < (MHSA_S / 2) * RV) k14[idx] = r14[i];
+    }
+    if (tid == 0) {
+      int len = a.mhsa_len[slot];
+      a.len_in[b] = len;
+      a.mhsa_len[slot] = min(len + a.T, MHSA_S);   // conformer_blocks.py:191
+    }
+  }
+
+  // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
+  __half* pre = a.pre + (size_t)slot * HOP;
+  const int* pcm = a.pcm + (size_t)b * C;
+  for (int i = tid; i < C + HOP; i += BEGIN_THREADS) {
+    float v;
+    if (i < HOP) v = __half2float(pre[i]);
+    else v = __half2float(__float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f));
+    u[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = __float2half_rn(u[C + i]);
+
+  // ---- framed DFT through the fused (pre-emphasis x Hann x DFT) basis: spec[f][k] = sum_j u[80 f + j] * basis[j][k]
+  {
+    const int half = (F + 1) / 2;
+    const int grp = tid / 162;            // 0, 1 (threads >= 324 idle here)
+    const int k = tid - grp * 162;
+    if (grp < 2) {
+      const int f0 = grp * half;
+      const int nf = min(half, F - f0);
+      float acc[MAX_FRAMES / 2];
+#pragma unroll
+      for (int f = 0; f < MAX_FRAMES / 2; ++f) acc[f] = 0.f;
+      for (int j = 0; j < WIN; j += 4) {
+        const float b0 = a.basis[(j + 0) * 162 + k], b1 = a.basis[(j + 1) * 162 + k];
+        const float b2 = a.basis[(j + 2) * 162 + k], b3 = a.basis[(j + 3) * 162 + k];
+#pragma unroll
+        for (int f = 0; f < MAX_FRAMES / 2; ++f) {
+          if (f < nf) {
+            const float4 y = *reinterpret_cast<const float4*>(&u[(f0 + f) * HOP + j]);
+            acc[f] = fmaf(b0, y.x, acc[f]);
+            acc[f] = fmaf(b1, y.y, acc[f]);
+            acc[f] = fmaf(b2, y.z, acc[f]);
+            acc[f] = fmaf(b3, y.w, acc[f]);
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < MAX_FRAMES / 2; ++f)
+        if (f < nf) spec[(f0 + f) * 162 + k] = acc[f];
+    }
+  }
+  __syncthreads();
+  // ---- power -> mel -> log (feats.py:99-101)
+  for (int i = tid; i < F * N_MELS; i += BEGIN_THREADS) {
+    const int f = i / N_MELS, m = i - f * N_MELS;
+    const float* sp = spec + f * 162;
+    float e = 0.f;
+    for (int p = a.mel_start[m]; p < a.mel_start[m + 1]; ++p) {
+      const int kb = a.mel_bin[p];
+      const float re = sp[kb], im = sp[N_BINS + kb];
+      e = fmaf(a.mel_w[p], re * re + im * im, e);
+    }
+    featS[i] = logf(e + 5.9604644775390625e-08f);   // 2^-24
+  }
+  __syncthreads();
+  // ---- RMSNorm(64) per frame (conformer_blocks.py:632, submodules.py:45-54), bf16 rows behind the 10 cached rows
+  bf16* frow = a.feat + ((size_t)slot * FEAT_ROWS_MAX + SUB1_ROWS) * N_MELS;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int f = warp; f < F; f += BEGIN_THREADS / 32) {
+    const float x0 = featS[f * N_MELS + lane], x1 = featS[f * N_MELS + 32 + lane];
+    const float ss = warp_sum(x0 * x0 + x1 * x1);
+    const float inv = 1.0f / (sqrtf(ss) * 0.125f + 1e-8f);
+    frow[f * N_MELS + lane] = __float2bfloat16(a.pre_norm_g[lane] * (x0 * inv));
+    frow[f * N_MELS + 32 + lane] = __float2bfloat16(a.pre_norm_g[32 + lane] * (x1 * inv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm(384)
+// One warp per row.  x = r[row]; if g1: x = g1*x/(rms+eps) and r[row] = x (the layer's norm_out, in place);
+// if g2: y = g2*x/(rms+eps) else y = x; n[row] = bf16(y).  Optionally the same bf16 row is scattered into the
+// stream's [cache | new] attention rows (layers 14/15 cache the NORMALISED layer input, submodules.py:295-303).
+struct NormArgs {
+  float* r;
+  const float* g1;
+  const float* g2;
+  bf16* n;
+  int M;
+  bf16* kv;            // nullable
+  const int* slots;
+  int rows_per_stream; // T of this layer
+  int kv_row_off;      // S
+};
+
+__device__ __forceinline__ float rms_inv_384(const float4 (&x)[3]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ss += x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+  ss = warp_sum(ss);
+  return 1.0f / (sqrtf(ss) * 0.05103103630798288f + 1e-8f);   // 384^-1/2
+}
+
+__device__ __forceinline__ void scale_384(float4 (&x)[3], const float* g, float inv, int lane) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i * 128 + lane * 4);
+    x[i].x = gg.x * (x[i].x * inv);
+    x[i].y = gg.y * (x[i].y * inv);
+    x[i].z = gg.z * (x[i].z * inv);
+    x[i].w = gg.w * (x[i].w * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= a.M) return;
+  float* rr = a.r + (size_t)row * D_MODEL;
+  float4 x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rr + i * 128 + lane * 4);
+  if (a.g1) {
+    scale_384(x, a.g1, rms_inv_384(x), lane);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = x[i];
+  }
+  if (a.g2) scale_384(x, a.g2, rms_inv_384(x), lane);
+  if (a.n) {
+    bf16* nr = a.n + (size_t)row * D_MODEL;
+    bf16* kr = nullptr;
+    if (a.kv) {
+      const int b = row / a.rows_per_stream, t = row - b * a.rows_per_stream;
+      kr = a.kv + ((size_t)a.slots[b] * KV_ROWS_MAX + a.kv_row_off + t) * D_MODEL;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      uint2 p = make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+      *reinterpret_cast<uint2*>(nr + i * 128 + lane * 4) = p;
+      if (kr) *reinterpret_cast<uint2*>(kr + i * 128 + lane * 4) = p;
+    }
+  }
+}
+
+// After layer 14: r_full[b,t] = (t < 2*T2 ? norm_out14(r_red[b, t/2]) : 0) + r_full[b,t]  (conformer_blocks.py:955-988),
+// followed by layer 15's first RMSNorm -> n (bf16).  One warp per full-rate row.
+struct UpsampleArgs {
+  float* r_full;
+  const float* r_red;
+  const float* g_out;   // norm_out of layer 14
+  const float* g_next;  // norm_feed_forward1 of layer 15
+  bf16* n;
+  int B, T, T2;
+};
+
+__global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= a.B * a.T) return;
+  const int b = row / a.T, t = row - b * a.T;
+  float* rr = a.r_full + (size_t)row * D_MODEL;
+  float4 x[3], y[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = *reinterpret_cast<const float4*>(rr + i * 128 + lane * 4);
+  if (t < 2 * a.T2) {
+    const float* rs = a.r_red + ((size_t)b * a.T2 + (t >> 1)) * D_MODEL;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rs + i * 128 + lane * 4);
+    scale_384(x, a.g_out, rms_inv_384(x), lane);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      y[i].x += x[i].x;
+      y[i].y += x[i].y;
+      y[i].z += x[i].z;
+      y[i].w += x[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = y[i];
+  scale_384(y, a.g_next, rms_inv_384(y), lane);
+  bf16* nr = a.n + (size_t)row * D_MODEL;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    *reinterpret_cast<uint2*>(nr + i * 128 + lane * 4) =
+        make_uint2(pack_bf16x2(y[i].x, y[i].y), pack_bf16x2(y[i].z, y[i].w));
+}
+
+// ------------------------------------------------------------------------------------------------ attention core
+struct AttnArgs {
+  const float* q; int ldq;    // [B*T][ldq]      (used when recompute)
+  const float* k; int ldk;    // [B*Tk][ldk]
+  const float* v; int ldv;    // [B*Tk][ldv]
+  float* P;                   // [B][8][T][Tk] probabilities shared by the following non-recompute layers
+  bf16* ctx;                  // [B*T][384]
+  const float* q_ln_w; const float* q_ln_b;
+  const float* k_ln_w; const float* k_ln_b;
+  const float* rope_cos;      // [MHSA_S + MAX_T][16], position p at row p + MHSA_S
+  const float* rope_sin;
+  const int* len_in;          // [B]
+  int T, Tk, S;
+  int recompute;
+  int mask_mode;              // 0 none, 1: off = 30 - len (layer 15), 2: off = (30 - len) / 2 (layer 14)
+};
+
+__device__ __forceinline__ void ln_rope_row(const float* src, const float* w, const float* bia, const float* cs,
+                                            const float* sn, float scale, float* dst) {
+  float x[D_HEAD];
+#pragma unroll
+  for (int i = 0; i < D_HEAD; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + i);
+    x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w;
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < D_HEAD; ++i) mean += x[i];
+  mean *= (1.0f / D_HEAD);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < D_HEAD; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+  const float inv = rsqrtf(var * (1.0f / D_HEAD) + 1e-5f);   // nn.LayerNorm(48), submodules.py:200-201
+#pragma unroll
+  for (int i = 0; i < D_HEAD; ++i) x[i] = (x[i] - mean) * inv * w[i] + bia[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {                              // RoPE on dims [0,32): pairs (i, i+16)
+    const float c = cs[i], s = sn[i];
+    const float x1 = x[i], x2 = x[i + 16];
+    x[i] = x1 * c - x2 * s;
+    x[i + 16] = x2 * c + x1 * s;
+  }
+#pragma unroll
+  for (int i = 0; i < D_HEAD; ++i) dst[i] = x[i] * scale;
+}
+
+__global__ void __launch_bounds__(64) attention_kernel(const AttnArgs a) {
+  __shared__ float qs[MAX_T][D_HEAD];
+  __shared__ float ks[MHSA_S + MAX_T][D_HEAD + 1];
+  __shared__ float ps[MAX_T][MHSA_S + MAX_T + 1];
+  const int b = blockIdx.x / N_HEADS, h = blockIdx.x - b * N_HEADS;
+  const int tid = threadIdx.x;
+  const int T = a.T, Tk = a.Tk, S = a.S;
+  float* Pg = a.P + ((size_t)(b * N_HEADS + h) * T) * Tk;
+
+  if (a.recompute) {
+    if (tid < T) {
+      ln_rope_row(a.q + (size_t)(b * T + tid) * a.ldq + h * D_HEAD, a.q_ln_w, a.q_ln_b,
+                  a.rope_cos + (tid + MHSA_S) * 16, a.rope_sin + (tid + MHSA_S) * 16,
+                  0.14433756729740643f /* 1/sqrt(48) */, qs[tid]);
+    } else if (tid < T + Tk) {
+      const int j = tid - T;                                   // key position j - S (submodules.py:136)
+      ln_rope_row(a.k + (size_t)(b * Tk + j) * a.ldk + h * D_HEAD, a.k_ln_w, a.k_ln_b,
+                  a.rope_cos + (j - S + MHSA_S) * 16, a.rope_sin + (j - S + MHSA_S) * 16, 1.0f, ks[j]);
+    }
+    __syncthreads();
+    int off = 0;
+    if (a.mask_mode == 1) off = MHSA_S - a.len_in[b];
+    else if (a.mask_mode == 2) off = (MHSA_S - a.len_in[b]) / 2;
+    if (tid < Tk) {
+      float kr[D_HEAD];
+#pragma unroll
+      for (int d = 0; d < D_HEAD; ++d) kr[d] = ks[tid][d];
+      const bool masked = tid < off;                           // cache columns older than the stream
+      for (int t = 0; t < T; ++t) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D_HEAD; ++d) s = fmaf(qs[t][d], kr[d], s);
+        ps[t][tid] = masked ? -10000.0f : s;                   // submodules.py:261
+      }
+    }
+    __syncthreads();
+    if (tid < T) {
+      float mx = -INFINITY;
+      for (int j = 0; j < Tk; ++j) mx = fmaxf(mx, ps[tid][j]);
+      float sum = 0.f;
+      for (int j = 0; j < Tk; ++j) {
+        const float e = expf(ps[tid][j] - mx);
+        ps[tid][j] = e;
+        sum += e;
+      }
+      const float inv = 1.0f / sum;
+      for (int j = 0; j < Tk; ++j) {
+        const float p = (j < off) ? 0.f : ps[tid][j] * inv;    // submodules.py:262
+        ps[tid][j] = p;
+        Pg[tid * Tk + j] = p;
+      }
+    }
+  } else {
+    for (int i = tid; i < T * Tk; i += 64) ps[i / Tk][i % Tk] = Pg[i];
+  }
+  __syncthreads();
+  if (tid < D_HEAD) {
+    float acc[MAX_T];
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t) acc[t] = 0.f;
+    const float* vp = a.v + (size_t)b * Tk * a.ldv + h * D_HEAD + tid;
+    for (int j = 0; j < Tk; ++j) {
+      const float vj = vp[(size_t)j * a.ldv];
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t)
+        if (t < T) acc[t] = fmaf(ps[t][j], vj, acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t)
+      if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + h * D_HEAD + tid] = __float2bfloat16(acc[t]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise conv
+struct DwArgs {
+  const bf16* g;        // [B*T][384] GLU output of this layer
+  bf16* cache;          // [slots][16][30][384] (layer offset already applied), time-major
+  long long cache_slot_stride;
+  const int* slots;
+  const float* w;       // [31][384] BN-folded taps
+  const float* bias;    // [384]     BN-folded bias
+  bf16* e;              // [B*T][384]
+  int T;
+};
+
+__global__ void __launch_bounds__(96) dwconv_kernel(const DwArgs a) {
+  const int b = blockIdx.x;
+  const int c = (blockIdx.y * 96 + threadIdx.x) * 2;         // two adjacent channels per thread
+  const int T = a.T;
+  bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride;
+  float2 col[CONV_S + MAX_T];
+#pragma unroll
+  for (int i = 0; i < CONV_S; ++i)
+    col[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(cache + i * D_MODEL + c));
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t)
+    if (t < T)
+      col[CONV_S + t] =
+          __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.g + (size_t)(b * T + t) * D_MODEL + c));
+  float2 acc[MAX_T];
+  const float2 bb = *reinterpret_cast<const float2*>(a.bias + c);
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t) acc[t] = bb;
+#pragma unroll
+  for (int j = 0; j <= CONV_S; ++j) {
+    const float2 wj = *reinterpret_cast<const float2*>(a.w + j * D_MODEL + c);
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t)
+      if (t < T) {
+        acc[t].x = fmaf(wj.x, col[t + j].x, acc[t].x);
+        acc[t].y = fmaf(wj.y, col[t + j].y, acc[t].y);
+      }
+  }
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t)
+    if (t < T)
+      *reinterpret_cast<__nv_bfloat162*>(a.e + (size_t)(b * T + t) * D_MODEL + c) =
+          __floats2bfloat162_rn(silu_f(acc[t].x), silu_f(acc[t].y));
+  // new cache = last 30 columns of [cache | g]  (submodules.py:364-370)
+#pragma unroll
+  for (int i = 0; i < CONV_S; ++i) {
+    float2 vsel = col[i];
+#pragma unroll
+    for (int t = 1; t <= MAX_T; ++t)
+      if (t == T) vsel = col[i + t];
+    *reinterpret_cast<__nv_bfloat162*>(cache + i * D_MODEL + c) = __floats2bfloat162_rn(vsel.x, vsel.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ temporal reduction
+// m[4c+k, t2] = b[4c+k] + sum_j W[4c+k][j] * v[c][2 t2 + j],  v = [red | r^T]  (conformer_blocks.py:874-911).
+struct RedArgs {
+  const float* r;       // [B*T][384] layer-6 output (norm_out applied)
+  float* red;           // [slots][384]
+  const int* slots;
+  const float* w;       // [1536][3]
+  const float* bias;    // [1536]
+  bf16* m;              // [B*T2][1536]
+  int T, T2;
+};
+
+__global__ void __launch_bounds__(D_MODEL) reduction_dw_kernel(const RedArgs a) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  float* red = a.red + (size_t)a.slots[b] * D_MODEL;
+  float w[12], bia[4];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) w[i] = a.w[c * 12 + i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bia[i] = a.bias[c * 4 + i];
+  float prev = red[c];
+  const float* r = a.r + (size_t)b * a.T * D_MODEL + c;
+  for (int t2 = 0; t2 < a.T2; ++t2) {
+    const float v0 = prev;                                    // v[c][2 t2]
+    const float v1 = r[(size_t)(2 * t2) * D_MODEL];           // v[c][2 t2 + 1] = r[2 t2]
+    const float v2 = r[(size_t)(2 * t2 + 1) * D_MODEL];       // v[c][2 t2 + 2] = r[2 t2 + 1]
+    prev = v2;
+    uint32_t p[2];
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = bia[k] + w[k * 3] * v0 + w[k * 3 + 1] * v1 + w[k * 3 + 2] * v2;
+    p[0] = pack_bf16x2(o[0], o[1]);
+    p[1] = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(a.m + ((size_t)b * a.T2 + t2) * (4 * D_MODEL) + c * 4) = make_uint2(p[0], p[1]);
+  }
+  red[c] = r[(size_t)(a.T - 1) * D_MODEL];                    // new state = last column of v
+}
+
+}  // namespace tone
