@@ -94,6 +94,13 @@ int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream);
 int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens);
 int tone_sync(tone_engine* e);
 
+/* Device-pointer form of the step for GPU-resident producers/consumers (the role of Triton's
+ * GPU tensors between ensemble stages, triton/ensemble/config.pbtxt:20-55): slots / pcm are
+ * device int32 buffers, logprobs / tokens device outputs (any may be NULL = use what is staged /
+ * leave in the engine).  Enqueued on `cuda_stream` (NULL = the engine's stream); asynchronous. */
+int tone_step_device(tone_engine* e, int32_t B, const int32_t* d_slots, const int32_t* d_pcm,
+                     float* d_logprobs, int32_t* d_tokens, void* cuda_stream);
+
 /* Pinned host staging buffers owned by the engine (slots [max_batch], pcm [max_batch][chunk],
  * logprobs [max_batch][T][35], tokens [max_batch][T]).  Passing these pointers to tone_step /
  * tone_stage / tone_fetch skips the intermediate host copy. */

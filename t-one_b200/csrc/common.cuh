@@ -32,6 +32,53 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ----------------------------------------------------------------------------- in-kernel timeline (diagnostic build only)
+// Built with -DTONE_PROF (libtone_b200_prof.so): block (0,0) of every kernel appends a record of timestamps, which
+// gives a launch-ordered timeline of a step without a tracing tool (nsys is not in this image).
+#ifdef TONE_PROF
+struct ProfRec {
+  unsigned long long g0, g1;      // %globaltimer at kernel start / end of block (0,0)
+  long long c[6];                 // clock64 marks inside the kernel, relative use
+  long long id;                   // kernel id: GEMM = 1000 + 100*KIND + BN/8 ; others 1..6
+  long long grid;                 // number of CTAs
+};
+__device__ ProfRec* g_prof = nullptr;
+__device__ unsigned int g_prof_n = 0;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF_DECL() __shared__ int prof_seq_s
+#define PROF_BEGIN(kid)                                                          \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_prof) {        \
+    prof_seq_s = (int)atomicAdd(&g_prof_n, 1u);                                  \
+    g_prof[prof_seq_s].id = (kid);                                               \
+    g_prof[prof_seq_s].grid = (long long)gridDim.x * gridDim.y;                  \
+    g_prof[prof_seq_s].g0 = gtimer();                                            \
+    g_prof[prof_seq_s].c[0] = clock64();                                         \
+  }
+#define PROF_MARK(i)                                                             \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && g_prof) g_prof[prof_seq_s].c[i] = clock64()
+#define PROF_END()                                                               \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_prof) {        \
+    g_prof[prof_seq_s].c[5] = clock64();                                         \
+    g_prof[prof_seq_s].g1 = gtimer();                                            \
+  }
+#else
+#define PROF_DECL()
+#define PROF_BEGIN(kid)
+#define PROF_MARK(i)
+#define PROF_END()
+#endif
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step is launched with programmatic stream serialization: it may start while its predecessor
+// is still running, does its private prologue (barrier init, TMEM alloc, weight prefetch), and blocks in
+// pdl_wait() until the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- smem / barriers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

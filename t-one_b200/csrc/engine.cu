@@ -136,6 +136,7 @@ struct tone_engine {
   float *r_full, *r_red, *qkv, *P, *logprobs;
   bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
   CUtensorMap m_feat, m_x1, m_kv14, m_kv15, m_n, m_h, m_ctx, m_e, m_c1, m_mred;
+  CUtensorMap w_feat, w_x1, w_kv14, w_kv15;   // same views with a box spanning the G slots of one tile
 
   // pinned staging
   int *p_slots, *p_pcm, *p_tokens;
@@ -143,6 +144,8 @@ struct tone_engine {
 
   std::unordered_map<int, cudaGraphExec_t> graphs;
   int launches = 0, launches_per_step = 0;
+  bool pdl = true;      // programmatic dependent launch between the kernels of a step (TONE_PDL=0 disables)
+  int num_sms = 148;
 };
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -249,6 +252,8 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
 
   tone_engine* e = new tone_engine();
   e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  if (const char* v = getenv("TONE_PDL")) e->pdl = atoi(v) != 0;
   e->C = cfg->chunk_samples;
   e->F = e->C / HOP;
   e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
@@ -308,20 +313,25 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   // activation-side tensor maps
   {
     uint64_t d[3] = {N_MELS, FEAT_ROWS_MAX, S}, s[2] = {N_MELS * 2, (uint64_t)FEAT_ROWS_MAX * N_MELS * 2};
-    uint32_t bx[3] = {64, (uint32_t)e->F, 1};
+    uint32_t bx[3] = {64, (uint32_t)e->F, 1}, bw[3] = {64, (uint32_t)e->F, (uint32_t)(128 / e->F)};
     if ((rc = make_map(e, &e->m_feat, e->st_feat, 3, d, s, bx, false))) return rc;
+    if ((rc = make_map(e, &e->w_feat, e->st_feat, 3, d, s, bw, false))) return rc;
   }
   {  // x1 as [slot][16 row triples][3 rows][1408]: conv1 frame t, kernel row kt reads row 3t+kt = triple t+kt/3, row kt%3
     uint64_t d[4] = {X1_ROW, 3, X1_ROWS_MAX / 3, S};
     uint64_t s[3] = {X1_ROW * 2, 3 * X1_ROW * 2, (uint64_t)X1_ROWS_MAX * X1_ROW * 2};
-    uint32_t bx[4] = {64, 1, (uint32_t)e->T, 1};
+    uint32_t bx[4] = {64, 1, (uint32_t)e->T, 1}, bw[4] = {64, 1, (uint32_t)e->T, (uint32_t)(128 / e->T)};
     if ((rc = make_map(e, &e->m_x1, e->st_x1, 4, d, s, bx, false))) return rc;
+    if ((rc = make_map(e, &e->w_x1, e->st_x1, 4, d, s, bw, false))) return rc;
   }
   {
     uint64_t d[3] = {D_MODEL, KV_ROWS_MAX, S}, s[2] = {D_MODEL * 2, (uint64_t)KV_ROWS_MAX * D_MODEL * 2};
     uint32_t b14[3] = {64, (uint32_t)(MHSA_S / 2 + e->T2), 1}, b15[3] = {64, (uint32_t)(MHSA_S + e->T), 1};
     if ((rc = make_map(e, &e->m_kv14, e->st_kv14, 3, d, s, b14, false))) return rc;
     if ((rc = make_map(e, &e->m_kv15, e->st_kv15, 3, d, s, b15, false))) return rc;
+    uint32_t w14[3] = {64, b14[1], 128 / b14[1]}, w15[3] = {64, b15[1], 128 / b15[1]};
+    if ((rc = make_map(e, &e->w_kv14, e->st_kv14, 3, d, s, w14, false))) return rc;
+    if ((rc = make_map(e, &e->w_kv15, e->st_kv15, 3, d, s, w15, false))) return rc;
   }
   if ((rc = make_map_2d(e, &e->m_n, e->n, R, D_MODEL, 128, false))) return rc;
   if ((rc = make_map_2d(e, &e->m_h, e->h, R, D_FF, 128, false))) return rc;
@@ -340,7 +350,8 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_CONV1, BN_CONV>()));
   CK((configure_gemm_tc<G_KV, BN_KV>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
-  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
   return TONE_OK;
 }
@@ -671,6 +682,7 @@ extern "C" int tone_finalize_weights(tone_engine* e) {
     if ((rc = upload_f32(e, db->data, &e->dec_b))) return rc;
   }
   e->host_w.clear();
+  CK(cudaDeviceSynchronize());   // pageable H2D copies may still be in flight when cudaMemcpy returns
   e->finalized = true;
   return TONE_OK;
 }
@@ -722,11 +734,12 @@ extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slot
 // ------------------------------------------------------------------------------------------------ the step
 template <int KIND, int BN>
 static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const WeightMat& w, GemmArgs a, int m_tiles,
-                int n_tiles, int ref_rows, int ref_cols) {
+                int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr) {
   a.W = w.ptr;
   a.ldw = w.K;
   cudaError_t err;
-  if (e->cfg.gemm_impl == 0) err = launch_gemm_tc<KIND, BN>(st, tmA, w.map, a, m_tiles, n_tiles);
+  if (e->cfg.gemm_impl == 0)
+    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, w.map, a, m_tiles, n_tiles, e->pdl, e->num_sms);
   else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols);
   e->launches++;
   if (err != cudaSuccess) return fail(TONE_ECUDA, "gemm kind %d launch: %s", KIND, cudaGetErrorString(err));
@@ -754,18 +767,17 @@ static GemmArgs dense_args(int M, int K, const bf16* A, void* out, int ldo, cons
     int _rc = (x);         \
     if (_rc) return _rc;   \
   } while (0)
-#define KLAUNCH()                                                                                       \
+#define KLAUNCH(call)                                                                                   \
   do {                                                                                                  \
     e->launches++;                                                                                      \
-    cudaError_t _e = cudaGetLastError();                                                                \
+    cudaError_t _e = (call);                                                                            \
     if (_e != cudaSuccess) return fail(TONE_ECUDA, "launch at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
   } while (0)
 
 static int run_norm(tone_engine* e, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
                     bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
   NormArgs a{r, g1, g2, n, M, kv, e->d_slots, rows_per_stream, kv_row_off};
-  norm_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
-  KLAUNCH();
+  KLAUNCH(launch_kernel(norm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
   return 0;
 }
 
@@ -810,9 +822,8 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     a.F = F;
     a.T = T;
     a.T2 = T2;
-    const size_t smem = (size_t)(C + HOP + F * 162 + F * N_MELS) * 4;
-    begin_step_kernel<<<B, BEGIN_THREADS, smem, st>>>(a);
-    KLAUNCH();
+    const size_t smem = (size_t)(C + HOP + F * 162 + F * N_MELS + WIN * 162) * 4;
+    KLAUNCH(launch_kernel(begin_step_kernel, dim3(B), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
   }
   {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels
     GemmArgs a;
@@ -830,7 +841,8 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     a.out_row_off = SUB2_ROWS;
     a.A = e->st_feat;
     a.a_slot_stride = FEAT_ROWS_MAX * N_MELS;
-    RC((gemm<G_CONV0, BN_CONV>(e, st, e->m_feat, e->conv0_w, a, (B + a.G - 1) / a.G, X1_ROW / BN_CONV, B * F, X1_ROW)));
+    RC((gemm<G_CONV0, BN_CONV>(e, st, e->m_feat, e->conv0_w, a, (B + a.G - 1) / a.G, X1_ROW / BN_CONV, B * F, X1_ROW,
+                               &e->w_feat)));
   }
   {  // conv1: rows = T frames per stream, K = 11 kernel rows x (12 positions x 32 channels), N = 2 positions x 64 ch
     GemmArgs a;
@@ -846,7 +858,8 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     a.beta = e->conv1_beta;
     a.A = e->st_x1;
     a.a_slot_stride = (long long)X1_ROWS_MAX * X1_ROW;
-    RC((gemm<G_CONV1, BN_CONV>(e, st, e->m_x1, e->conv1_w, a, (B + a.G - 1) / a.G, SUB_OUT / BN_CONV, B * T, SUB_OUT)));
+    RC((gemm<G_CONV1, BN_CONV>(e, st, e->m_x1, e->conv1_w, a, (B + a.G - 1) / a.G, SUB_OUT / BN_CONV, B * T, SUB_OUT,
+                               &e->w_x1)));
   }
   int M = B * T;
   {
@@ -917,7 +930,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
       k.lda = D_MODEL;
       k.a_slot_stride = KV_ROWS_MAX * D_MODEL;
       RC((gemm<G_KV, BN_KV>(e, st, l == 14 ? e->m_kv14 : e->m_kv15, L.kv, k, (B + k.G - 1) / k.G, 2 * D_MODEL / BN_KV,
-                            B * k.R, 2 * D_MODEL)));
+                            B * k.R, 2 * D_MODEL, l == 14 ? &e->w_kv14 : &e->w_kv15)));
       at.S = S;
       at.Tk = S + Tl;
       at.q = qbuf;
@@ -931,8 +944,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
       at.k_ln_b = L.kln_b;
       at.mask_mode = (l == 14) ? 2 : 1;
     }
-    attention_kernel<<<B * N_HEADS, 64, 0, st>>>(at);
-    KLAUNCH();
+    KLAUNCH(launch_kernel(attention_kernel, dim3(B * N_HEADS), dim3(64), 0, st, e->pdl, at));
     {
       GemmArgs a = dense_args(M, D_MODEL, e->ctx, r, D_MODEL, L.wo_b, 1.f);
       RC((gemm<G_RESID, BN_RESID>(e, st, e->m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
@@ -953,8 +965,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
       d.bias = L.dw_b;
       d.e = e->ebuf;
       d.T = Tl;
-      dwconv_kernel<<<dim3(B, 2), 96, 0, st>>>(d);
-      KLAUNCH();
+      KLAUNCH(launch_kernel(dwconv_kernel, dim3(B, 2), dim3(96), 0, st, e->pdl, d));
     }
     {
       GemmArgs a = dense_args(M, D_MODEL, e->ebuf, r, D_MODEL, L.pw2_b, 1.f);
@@ -966,8 +977,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     if (l == 6) {
       RC(run_norm(e, st, r, L.n_out, nullptr, nullptr, M));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{e->r_full, e->st_red, e->d_slots, e->red_dw_w, e->red_dw_b, e->m_red, T, T2};
-      reduction_dw_kernel<<<B, D_MODEL, 0, st>>>(ra);
-      KLAUNCH();
+      KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
       GemmArgs a = dense_args(M2, D_FF, e->m_red, e->r_red, D_MODEL, e->red_pw_b, 1.f);
       RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
@@ -975,8 +985,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
       RC(tap(1 + l, e->r_red, M2));
     } else if (l == 14) {
       UpsampleArgs ua{e->r_full, e->r_red, L.n_out, e->L[15].n_ff1, e->n, B, T, T2};
-      upsample_norm_kernel<<<(B * T + 7) / 8, 256, 0, st>>>(ua);
-      KLAUNCH();
+      KLAUNCH(launch_kernel(upsample_norm_kernel, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, e->r_full, B * T));
     } else if (l == 15) {
       RC(run_norm(e, st, r, L.n_out, nullptr, e->n, M));
@@ -1040,6 +1049,22 @@ extern "C" int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream) {
   RC(check_step_args(e, B));
   CK(cudaSetDevice(e->cfg.device));
   return launch_step(e, B, cuda_stream ? (cudaStream_t)cuda_stream : e->stream);
+}
+
+// Device-pointer form for GPU-resident producers/consumers: inputs are copied device-to-device into the engine's
+// staging (the captured graph reads fixed addresses), outputs are copied out the same way.  Stream-ordered, no sync.
+extern "C" int tone_step_device(tone_engine* e, int32_t B, const int32_t* d_slots, const int32_t* d_pcm,
+                                float* d_logprobs, int32_t* d_tokens, void* cuda_stream) {
+  RC(check_step_args(e, B));
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  if (d_slots) CK(cudaMemcpyAsync(e->d_slots, d_slots, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_pcm) CK(cudaMemcpyAsync(e->d_pcm, d_pcm, (size_t)B * e->C * 4, cudaMemcpyDeviceToDevice, st));
+  RC(launch_step(e, B, st));
+  if (d_logprobs)
+    CK(cudaMemcpyAsync(d_logprobs, e->logprobs, (size_t)B * e->T * N_CLASSES * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_tokens) CK(cudaMemcpyAsync(d_tokens, e->d_tokens, (size_t)B * e->T * 4, cudaMemcpyDeviceToDevice, st));
+  return TONE_OK;
 }
 
 extern "C" int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens) {
@@ -1171,6 +1196,7 @@ extern "C" int tone_import_state(tone_engine* e, int32_t slot, const uint16_t* i
   CK(cudaMemcpy(e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, conv.data(), conv.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->st_red + s * D_MODEL, red.data(), D_MODEL * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->st_len + s, &len, 4, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
   return TONE_OK;
 }
 
@@ -1183,7 +1209,8 @@ static int selftest_bn(tone_engine* e, int M, int N, int K, const bf16* dA, cons
   GemmArgs a = dense_args(M, K, dA, dC, N, nullptr, 1.f);
   a.W = dW;
   a.ldw = K;
-  cudaError_t err = launch_gemm_tc<G_STORE_F32, BN>(e->stream, ma, mw, a, (M + 127) / 128, N / BN);
+  CK(cudaDeviceSynchronize());   // operands were uploaded with cudaMemcpy from pageable memory
+  cudaError_t err = launch_gemm_tc<G_STORE_F32, BN>(e->stream, ma, ma, mw, a, (M + 127) / 128, N / BN, false, e->num_sms);
   if (err != cudaSuccess) return fail(TONE_ECUDA, "selftest launch: %s", cudaGetErrorString(err));
   return 0;
 }
@@ -1223,3 +1250,36 @@ extern "C" int tone_selftest_gemm(tone_engine* e, int32_t M, int32_t N, int32_t 
   cudaFree(dC);
   return rc;
 }
+
+// ------------------------------------------------------------------------------------------------ timeline (diagnostic build)
+#ifdef TONE_PROF
+static ProfRec* g_prof_dev = nullptr;
+static int g_prof_cap = 0;
+extern "C" int tone_prof_start(tone_engine* e, int32_t max_records) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  if (g_prof_dev) cudaFree(g_prof_dev);
+  CK(cudaMalloc((void**)&g_prof_dev, (size_t)max_records * sizeof(ProfRec)));
+  CK(cudaMemset(g_prof_dev, 0, (size_t)max_records * sizeof(ProfRec)));
+  g_prof_cap = max_records;
+  unsigned int zero = 0;
+  CK(cudaMemcpyToSymbol(g_prof_n, &zero, sizeof(zero)));
+  CK(cudaMemcpyToSymbol(g_prof, &g_prof_dev, sizeof(g_prof_dev)));
+  CK(cudaDeviceSynchronize());
+  return TONE_OK;
+}
+// out: [n][10] uint64 = g0, g1, c0..c5, id, grid ; returns the number of records through *n_out and stops recording
+extern "C" int tone_prof_read(tone_engine* e, unsigned long long* out, int32_t max_records, int32_t* n_out) {
+  if (!e || !out || !n_out) return fail(TONE_EINVAL, "null argument");
+  CK(cudaDeviceSynchronize());
+  unsigned int n = 0;
+  CK(cudaMemcpyFromSymbol(&n, g_prof_n, sizeof(n)));
+  ProfRec* none = nullptr;
+  CK(cudaMemcpyToSymbol(g_prof, &none, sizeof(none)));
+  int m = (int)std::min<unsigned int>(n, (unsigned int)std::min(max_records, g_prof_cap));
+  CK(cudaMemcpy(out, g_prof_dev, (size_t)m * sizeof(ProfRec), cudaMemcpyDeviceToHost));
+  *n_out = m;
+  return TONE_OK;
+}
+#endif

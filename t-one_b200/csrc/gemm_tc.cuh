@@ -10,6 +10,8 @@
 // cached-context K/V projections read [cache | new rows] in place.
 #pragma once
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace tone {
@@ -53,13 +55,15 @@ struct KindTraits {
   static constexpr bool gather = (KIND == G_CONV0 || KIND == G_CONV1 || KIND == G_KV);
 };
 
-template <int BN>
+// DEEP = one CTA per SM with the whole shared memory as the operand ring: the small-batch GEMMs of this model are
+// latency bound (few CTAs, short K loops), so all that matters is how many TMA loads are in flight.
+template <int BN, bool DEEP = true>
 struct TileCfg {
-  static constexpr int STAGES = (BN > 64) ? 3 : 4;
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGES = DEEP ? (200 * 1024) / (A_BYTES + B_BYTES) : ((BN > 64) ? 3 : 4);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024 + 1024;  // + barriers + constants + alignment slack
 };
 
 // ---------------------------------------------------------------------------------------------- epilogues
@@ -91,50 +95,76 @@ __device__ __forceinline__ RowInfo row_info(const GemmArgs& a, int row_in_tile) 
   return ri;
 }
 
+// Per-tile constants (bias, or folded BatchNorm scale/shift per output column) are staged in shared memory by the
+// epilogue warps while the main loop runs; they are weights, so this happens before the PDL wait.
 template <int KIND, int BN>
-__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int row_in_tile) {
+__device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..127*/) {
+  const int n0 = blockIdx.y * BN;
+  if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
+    constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
+    if (t < BN) {
+      s_c0[t] = __ldg(a.alpha + (n0 + t) % CH);
+      s_c1[t] = __ldg(a.beta + (n0 + t) % CH);
+    }
+  } else if constexpr (KIND == G_DECODER) {
+    if (t < 48) s_c0[t] = t < 35 ? __ldg(a.bias + t) : 0.f;
+  } else {
+    if (t < BN) s_c0[t] = a.bias ? __ldg(a.bias + n0 + t) : 0.f;
+  }
+}
+
+template <int KIND, int BN>
+__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int row_in_tile,
+                                         const float* s_c0, const float* s_c1, uint64_t* tmem_full) {
   const RowInfo ri = row_info<KIND>(a, row_in_tile);
   const int n0 = blockIdx.y * BN;
   float v[16];
   if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
-    float* out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
-#pragma unroll 1
+    float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
     for (int c = 0; c < BN; c += 16) {
       tmem_ld16(tmem_row_base + c, v);
       if (ri.valid) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 o;
-          o.x = v[i + 0] + (a.bias ? a.bias[n0 + c + i + 0] : 0.f);
-          o.y = v[i + 1] + (a.bias ? a.bias[n0 + c + i + 1] : 0.f);
-          o.z = v[i + 2] + (a.bias ? a.bias[n0 + c + i + 2] : 0.f);
-          o.w = v[i + 3] + (a.bias ? a.bias[n0 + c + i + 3] : 0.f);
-          *reinterpret_cast<float4*>(out + c + i) = o;
-        }
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(out + c + i) = make_float4(v[i] + s_c0[c + i], v[i + 1] + s_c0[c + i + 1],
+                                                                v[i + 2] + s_c0[c + i + 2], v[i + 3] + s_c0[c + i + 3]);
       }
     }
   } else if constexpr (KIND == G_RESID) {
-    float* out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
-#pragma unroll 1
+    // the residual row segment is fetched while the main loop runs
+    float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
+    float4 r[BN / 4];
+    if (ri.valid) {
+#pragma unroll
+      for (int i = 0; i < BN / 4; ++i) r[i] = *reinterpret_cast<const float4*>(out + 4 * i);
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
     for (int c = 0; c < BN; c += 16) {
       tmem_ld16(tmem_row_base + c, v);
       if (ri.valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          float4 o = *reinterpret_cast<float4*>(out + c + i);
-          o.x += a.scale * (v[i + 0] + a.bias[n0 + c + i + 0]);
-          o.y += a.scale * (v[i + 1] + a.bias[n0 + c + i + 1]);
-          o.z += a.scale * (v[i + 2] + a.bias[n0 + c + i + 2]);
-          o.w += a.scale * (v[i + 3] + a.bias[n0 + c + i + 3]);
+          float4 o = r[(c + i) / 4];
+          o.x += a.scale * (v[i + 0] + s_c0[c + i + 0]);
+          o.y += a.scale * (v[i + 1] + s_c0[c + i + 1]);
+          o.z += a.scale * (v[i + 2] + s_c0[c + i + 2]);
+          o.w += a.scale * (v[i + 3] + s_c0[c + i + 3]);
           *reinterpret_cast<float4*>(out + c + i) = o;
         }
       }
     }
   } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
     constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
-    bf16* out = reinterpret_cast<bf16*>(a.out) + ri.out_row * a.ldo + blockIdx.y * HW;
+    bf16* __restrict__ out = reinterpret_cast<bf16*>(a.out) + ri.out_row * a.ldo + blockIdx.y * HW;
     float w[16];
-#pragma unroll 1
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
     for (int c = 0; c < HW; c += 16) {
       tmem_ld16(tmem_row_base + c, v);
       tmem_ld16(tmem_row_base + HW + c, w);
@@ -142,8 +172,8 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         uint32_t p[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float x0 = v[i] + a.bias[n0 + c + i], x1 = v[i + 1] + a.bias[n0 + c + i + 1];
-          float y0 = w[i] + a.bias[n0 + HW + c + i], y1 = w[i + 1] + a.bias[n0 + HW + c + i + 1];
+          float x0 = v[i] + s_c0[c + i], x1 = v[i + 1] + s_c0[c + i + 1];
+          float y0 = w[i] + s_c0[HW + c + i], y1 = w[i + 1] + s_c0[HW + c + i + 1];
           float r0, r1;
           if constexpr (KIND == G_SWIGLU) {
             r0 = silu_f(x0) * y0;
@@ -160,20 +190,20 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       }
     }
   } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
-    // channel index of column n: conv0 n = f*32 + o (o = n % 32); conv1 tile column c = j*64 + o (o = c % 64)
-    constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
-    bf16* out = reinterpret_cast<bf16*>(a.out) +
-                (KIND == G_CONV0 ? ri.out_row : ri.out_row * (long long)a.ldo) + n0;
-#pragma unroll 1
+    // column n of conv0 is (f = n/32, o = n%32); tile column c of conv1 is (j = c/64, o = c%64)
+    bf16* __restrict__ out = reinterpret_cast<bf16*>(a.out) +
+                             (KIND == G_CONV0 ? ri.out_row : ri.out_row * (long long)a.ldo) + n0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
     for (int c = 0; c < BN; c += 16) {
       tmem_ld16(tmem_row_base + c, v);
       if (ri.valid) {
         uint32_t p[8];
-        const int ch0 = (n0 + c) % CH;
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float r0 = silu_f(v[i] * a.alpha[ch0 + i] + a.beta[ch0 + i]);
-          float r1 = silu_f(v[i + 1] * a.alpha[ch0 + i + 1] + a.beta[ch0 + i + 1]);
+          float r0 = silu_f(v[i] * s_c0[c + i] + s_c1[c + i]);
+          float r1 = silu_f(v[i + 1] * s_c0[c + i + 1] + s_c1[c + i + 1]);
           p[i / 2] = pack_bf16x2(r0, r1);
         }
         uint4* o = reinterpret_cast<uint4*>(out + c);
@@ -184,6 +214,8 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
   } else if constexpr (KIND == G_DECODER) {
     static_assert(KIND != G_DECODER || BN == 48, "decoder tile is 48 columns (35 classes + padding)");
     float lg[48];
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
     tmem_ld16(tmem_row_base + 0, lg);
     tmem_ld16(tmem_row_base + 16, lg + 16);
     tmem_ld16(tmem_row_base + 32, lg + 32);
@@ -192,17 +224,17 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       int am = 0;
 #pragma unroll
       for (int i = 0; i < 35; ++i) {
-        lg[i] += a.bias[i];
+        lg[i] += s_c0[i];
         if (lg[i] > mx) {  // strict > keeps the first maximum (numpy argmax, tone/decoder.py:57)
           mx = lg[i];
           am = i;
         }
       }
-      float s = 0.f;
+      float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 35; ++i) s += expf(lg[i] - mx);
-      const float lse = mx + logf(s);
-      float* out = reinterpret_cast<float*>(a.out) + ri.out_row * 35;
+      for (int i = 0; i < 35; ++i) sum += expf(lg[i] - mx);
+      const float lse = mx + logf(sum);
+      float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * 35;
 #pragma unroll
       for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
       if (a.tokens) a.tokens[ri.out_row] = am;
@@ -211,10 +243,11 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int KIND, int BN>
+template <int KIND, int BN, bool DEEP>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmAw,
                                                       const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,10 +257,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_c0 = reinterpret_cast<float*>(sB + STAGES * Cfg::B_BYTES + 256);   // per-column constants of this tile
+  float* s_c1 = s_c0 + 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  PROF_DECL();
+  PROF_BEGIN(1000 + 100 * KIND + BN / 8);
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -243,6 +281,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) PROF_MARK(1);   // prologue done
 
   if (warp == 0) {
     if (lane == 0) {
@@ -253,31 +292,58 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         nvalid = nvalid > a.G ? a.G : nvalid;
       }
       const uint32_t a_bytes = KindTraits<KIND>::gather ? (uint32_t)(nvalid * a.R * 128) : (uint32_t)Cfg::A_BYTES;
+      const int b_row = (KIND == G_CONV1) ? 0 : blockIdx.y * BN;
+      // The weight tiles do not depend on the previous kernel: put the first ring of them in flight, then wait for
+      // the predecessor grid before touching activations.
+      const int npre = a.nk < STAGES ? a.nk : STAGES;
+      for (int it = 0; it < npre; ++it) {
+        mbar_expect_tx(&full[it], a_bytes + Cfg::B_BYTES);
+        tma_load_2d(sB + it * Cfg::B_BYTES, &tmB, &full[it], it * 64, b_row);
+      }
+      pdl_wait();
+      PROF_MARK(2);                     // predecessor grid complete
+      // Gather tiles whose G streams sit in consecutive slots load all of them with ONE wide box per K step
+      // (tmAw: same view, box spans G slots); otherwise one box per stream.
+      bool wide = false;
+      int slot0 = 0;
+      if constexpr (KindTraits<KIND>::gather) {
+        slot0 = a.slots[blockIdx.x * a.G];
+        wide = (nvalid == a.G);
+        for (int g = 1; g < nvalid; ++g) wide = wide && (a.slots[blockIdx.x * a.G + g] == slot0 + g);
+      }
       for (int it = 0; it < a.nk; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
+        if (it >= npre) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
+          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], it * 64, b_row);
+        }
         uint8_t* dA = sA + s * Cfg::A_BYTES;
         if constexpr (KIND == G_CONV0) {
           // K iteration = kernel row kt; box = 64 mel bins x R frames starting at feature row kt
-          for (int g = 0; g < nvalid; ++g)
-            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], 0, it, a.slots[blockIdx.x * a.G + g]);
+          if (wide) tma_load_3d(dA, &tmAw, &full[s], 0, it, slot0);
+          else
+            for (int g = 0; g < nvalid; ++g)
+              tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], 0, it, a.slots[blockIdx.x * a.G + g]);
         } else if constexpr (KIND == G_CONV1) {
           // K iteration = (kt, 64-wide piece kc of the 12-position x 32-channel window at f0 = 2*blockIdx.y).
           // x1 is viewed as [slot][row triple][row in triple][44*32]; output frame t reads row 3t + kt, so the
           // box walks R consecutive triples starting at kt/3 with the in-triple row fixed to kt%3.
           const int kt = it / 6, kc = it - kt * 6;
-          for (int g = 0; g < nvalid; ++g)
-            tma_load_4d(dA + g * a.R * 128, &tmA, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3,
-                        a.slots[blockIdx.x * a.G + g]);
+          if (wide) tma_load_4d(dA, &tmAw, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3, slot0);
+          else
+            for (int g = 0; g < nvalid; ++g)
+              tma_load_4d(dA + g * a.R * 128, &tmA, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3,
+                          a.slots[blockIdx.x * a.G + g]);
         } else if constexpr (KIND == G_KV) {
-          for (int g = 0; g < nvalid; ++g)
-            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
+          if (wide) tma_load_3d(dA, &tmAw, &full[s], it * 64, 0, slot0);
+          else
+            for (int g = 0; g < nvalid; ++g)
+              tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
         } else {
           tma_load_2d(dA, &tmA, &full[s], it * 64, blockIdx.x * 128);
         }
-        tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], it * 64, (KIND == G_CONV1) ? 0 : blockIdx.y * BN);
       }
     }
   } else if (warp == 1) {
@@ -288,6 +354,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
+        if (it == 0) PROF_MARK(3);      // first operand stage landed
         tc_fence_after();
         const uint64_t da = make_sw128_desc(smem_u32(sA + s * Cfg::A_BYTES));
         const uint64_t db = make_sw128_desc(smem_u32(sB + s * Cfg::B_BYTES));
@@ -301,28 +368,57 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   } else {
     // ---------------- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q * 32 + lane);
+    stage_constants<KIND, BN>(a, s_c0, s_c1, threadIdx.x - 64);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    pdl_wait();
+    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q * 32 + lane, s_c0, s_c1, tmem_full);
+    if (threadIdx.x == 64) PROF_MARK(4);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  PROF_END();
+}
+
+// Launch with (optional) programmatic stream serialization.
+template <typename Kern, typename... Args>
+inline cudaError_t launch_kernel(Kern kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // Must be called once per instantiation (outside stream capture) before the first launch.
 template <int KIND, int BN>
 inline cudaError_t configure_gemm_tc() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              TileCfg<BN>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       TileCfg<BN, true>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TileCfg<BN, false>::SMEM_BYTES);
 }
 
+// deep = one CTA per SM, whole smem as the ring (grids that fit in one wave); otherwise two CTAs per SM.
 template <int KIND, int BN>
-inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                                  const GemmArgs& a, int m_tiles, int n_tiles) {
-  using Cfg = TileCfg<BN>;
-  gemm_tc_kernel<KIND, BN><<<dim3(m_tiles, n_tiles), 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
-  return cudaGetLastError();
+inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmAw,
+                                  const CUtensorMap& tmB, const GemmArgs& a, int m_tiles, int n_tiles, bool pdl,
+                                  int num_sms) {
+  const dim3 grid(m_tiles, n_tiles);
+  if (m_tiles * n_tiles <= 2 * num_sms)
+    return launch_kernel(gemm_tc_kernel<KIND, BN, true>, grid, dim3(192), TileCfg<BN, true>::SMEM_BYTES, st, pdl, tmA,
+                         tmAw, tmB, a);
+  return launch_kernel(gemm_tc_kernel<KIND, BN, false>, grid, dim3(192), TileCfg<BN, false>::SMEM_BYTES, st, pdl, tmA,
+                       tmAw, tmB, a);
 }
 
 }  // namespace tone

@@ -54,12 +54,32 @@ struct BeginArgs {
 constexpr int BEGIN_THREADS = 352;
 
 __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  PROF_DECL();
+  PROF_BEGIN(1);
+  pdl_launch_dependents();
   const int F = a.F, C = a.C;
   float* u = sm;                          // [C + 80]
   float* spec = u + (C + 80);             // [F][162]
   float* featS = spec + F * 162;          // [F][64]
+  float* basisS = featS + F * N_MELS;     // [160][162] constant basis, staged before the PDL wait
   const int b = blockIdx.x, tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.basis);
+    float4* dst = reinterpret_cast<float4*>(basisS);
+    constexpr int N4 = WIN * 162 / 4;     // 6480
+    for (int i0 = 0; i0 < N4; i0 += 4 * BEGIN_THREADS) {
+      float4 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i0 + q * BEGIN_THREADS + tid < N4) t[q] = __ldg(src + i0 + q * BEGIN_THREADS + tid);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i0 + q * BEGIN_THREADS + tid < N4) dst[i0 + q * BEGIN_THREADS + tid] = t[q];
+    }
+  }
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int slot = a.slots[b];
 
   // ---- start-of-step cache rolls: the last rows of [cache | previous new rows] become the cache
@@ -112,6 +132,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     u[i] = v;
   }
   __syncthreads();
+  if (threadIdx.x == 0) PROF_MARK(1);
   for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = __float2half_rn(u[C + i]);
 
   // ---- framed DFT through the fused (pre-emphasis x Hann x DFT) basis: spec[f][k] = sum_j u[80 f + j] * basis[j][k]
@@ -126,8 +147,8 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
 #pragma unroll
       for (int f = 0; f < MAX_FRAMES / 2; ++f) acc[f] = 0.f;
       for (int j = 0; j < WIN; j += 4) {
-        const float b0 = a.basis[(j + 0) * 162 + k], b1 = a.basis[(j + 1) * 162 + k];
-        const float b2 = a.basis[(j + 2) * 162 + k], b3 = a.basis[(j + 3) * 162 + k];
+        const float b0 = basisS[(j + 0) * 162 + k], b1 = basisS[(j + 1) * 162 + k];
+        const float b2 = basisS[(j + 2) * 162 + k], b3 = basisS[(j + 3) * 162 + k];
 #pragma unroll
         for (int f = 0; f < MAX_FRAMES / 2; ++f) {
           if (f < nf) {
@@ -145,6 +166,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) PROF_MARK(3);
   // ---- power -> mel -> log (feats.py:99-101)
   for (int i = tid; i < F * N_MELS; i += BEGIN_THREADS) {
     const int f = i / N_MELS, m = i - f * N_MELS;
@@ -158,6 +180,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     featS[i] = logf(e + 5.9604644775390625e-08f);   // 2^-24
   }
   __syncthreads();
+  if (threadIdx.x == 0) PROF_MARK(4);
   // ---- RMSNorm(64) per frame (conformer_blocks.py:632, submodules.py:45-54), bf16 rows behind the 10 cached rows
   bf16* frow = a.feat + ((size_t)slot * FEAT_ROWS_MAX + SUB1_ROWS) * N_MELS;
   const int warp = tid >> 5, lane = tid & 31;
@@ -168,6 +191,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     frow[f * N_MELS + lane] = __float2bfloat16(a.pre_norm_g[lane] * (x0 * inv));
     frow[f * N_MELS + 32 + lane] = __float2bfloat16(a.pre_norm_g[32 + lane] * (x1 * inv));
   }
+  PROF_END();
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm(384)
@@ -206,6 +230,11 @@ __device__ __forceinline__ void scale_384(float4 (&x)[3], const float* g, float 
 }
 
 __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
+  PROF_DECL();
+  PROF_BEGIN(2);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= a.M) return;
@@ -233,6 +262,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
       if (kr) *reinterpret_cast<uint2*>(kr + i * 128 + lane * 4) = p;
     }
   }
+  PROF_END();
 }
 
 // After layer 14: r_full[b,t] = (t < 2*T2 ? norm_out14(r_red[b, t/2]) : 0) + r_full[b,t]  (conformer_blocks.py:955-988),
@@ -247,6 +277,11 @@ struct UpsampleArgs {
 };
 
 __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a) {
+  PROF_DECL();
+  PROF_BEGIN(3);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= a.B * a.T) return;
@@ -276,6 +311,7 @@ __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a
   for (int i = 0; i < 3; ++i)
     *reinterpret_cast<uint2*>(nr + i * 128 + lane * 4) =
         make_uint2(pack_bf16x2(y[i].x, y[i].y), pack_bf16x2(y[i].z, y[i].w));
+  PROF_END();
 }
 
 // ------------------------------------------------------------------------------------------------ attention core
@@ -328,11 +364,32 @@ __global__ void __launch_bounds__(64) attention_kernel(const AttnArgs a) {
   __shared__ float qs[MAX_T][D_HEAD];
   __shared__ float ks[MHSA_S + MAX_T][D_HEAD + 1];
   __shared__ float ps[MAX_T][MHSA_S + MAX_T + 1];
+  __shared__ __align__(16) float vs[MHSA_S + MAX_T][D_HEAD];
+  PROF_DECL();
+  PROF_BEGIN(4);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int b = blockIdx.x / N_HEADS, h = blockIdx.x - b * N_HEADS;
   const int tid = threadIdx.x;
   const int T = a.T, Tk = a.Tk, S = a.S;
   float* Pg = a.P + ((size_t)(b * N_HEADS + h) * T) * Tk;
 
+  // V tile [Tk][48] -> smem: 12 float4 per row, independent loads issued up front
+  {
+    float4 tmp[9];
+    const float* vp = a.v + (size_t)b * Tk * a.ldv + h * D_HEAD;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int idx = tid + i * 64;
+      if (idx < Tk * 12) tmp[i] = *reinterpret_cast<const float4*>(vp + (size_t)(idx / 12) * a.ldv + (idx % 12) * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int idx = tid + i * 64;
+      if (idx < Tk * 12) *reinterpret_cast<float4*>(&vs[idx / 12][(idx % 12) * 4]) = tmp[i];
+    }
+  }
   if (a.recompute) {
     if (tid < T) {
       ln_rope_row(a.q + (size_t)(b * T + tid) * a.ldq + h * D_HEAD, a.q_ln_w, a.q_ln_b,
@@ -377,16 +434,23 @@ __global__ void __launch_bounds__(64) attention_kernel(const AttnArgs a) {
       }
     }
   } else {
-    for (int i = tid; i < T * Tk; i += 64) ps[i / Tk][i % Tk] = Pg[i];
+    float tmp[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (tid + i * 64 < T * Tk) tmp[i] = Pg[tid + i * 64];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int idx = tid + i * 64;
+      if (idx < T * Tk) ps[idx / Tk][idx % Tk] = tmp[i];
+    }
   }
   __syncthreads();
   if (tid < D_HEAD) {
     float acc[MAX_T];
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t) acc[t] = 0.f;
-    const float* vp = a.v + (size_t)b * Tk * a.ldv + h * D_HEAD + tid;
     for (int j = 0; j < Tk; ++j) {
-      const float vj = vp[(size_t)j * a.ldv];
+      const float vj = vs[j][tid];
 #pragma unroll
       for (int t = 0; t < MAX_T; ++t)
         if (t < T) acc[t] = fmaf(ps[t][j], vj, acc[t]);
@@ -395,6 +459,7 @@ __global__ void __launch_bounds__(64) attention_kernel(const AttnArgs a) {
     for (int t = 0; t < MAX_T; ++t)
       if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + h * D_HEAD + tid] = __float2bfloat16(acc[t]);
   }
+  PROF_END();
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise conv
@@ -410,6 +475,11 @@ struct DwArgs {
 };
 
 __global__ void __launch_bounds__(96) dwconv_kernel(const DwArgs a) {
+  PROF_DECL();
+  PROF_BEGIN(5);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int b = blockIdx.x;
   const int c = (blockIdx.y * 96 + threadIdx.x) * 2;         // two adjacent channels per thread
   const int T = a.T;
@@ -451,6 +521,7 @@ __global__ void __launch_bounds__(96) dwconv_kernel(const DwArgs a) {
       if (t == T) vsel = col[i + t];
     *reinterpret_cast<__nv_bfloat162*>(cache + i * D_MODEL + c) = __floats2bfloat162_rn(vsel.x, vsel.y);
   }
+  PROF_END();
 }
 
 // ------------------------------------------------------------------------------------------------ temporal reduction
@@ -466,6 +537,11 @@ struct RedArgs {
 };
 
 __global__ void __launch_bounds__(D_MODEL) reduction_dw_kernel(const RedArgs a) {
+  PROF_DECL();
+  PROF_BEGIN(6);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   const int b = blockIdx.x, c = threadIdx.x;
   float* red = a.red + (size_t)a.slots[b] * D_MODEL;
   float w[12], bia[4];
@@ -489,6 +565,7 @@ __global__ void __launch_bounds__(D_MODEL) reduction_dw_kernel(const RedArgs a) 
     *reinterpret_cast<uint2*>(a.m + ((size_t)b * a.T2 + t2) * (4 * D_MODEL) + c * 4) = make_uint2(p[0], p[1]);
   }
   red[c] = r[(size_t)(a.T - 1) * D_MODEL];                    // new state = last column of v
+  PROF_END();
 }
 
 }  // namespace tone

@@ -19,7 +19,7 @@ from .arch import DEFAULT_ARCH
 from . import weights as _weights
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtone_b200.so")
+LIB_PATH = os.environ.get("TONE_B200_LIB") or os.path.join(_HERE, "libtone_b200.so")
 
 TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1, -2, -3, -4, -5
 
@@ -27,7 +27,7 @@ TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1,
 SYMBOLS = (
     "tone_create", "tone_destroy", "tone_get_info", "tone_last_error", "tone_load_weight",
     "tone_finalize_weights", "tone_alloc_slots", "tone_release_slots", "tone_reset_slots", "tone_step",
-    "tone_stage", "tone_step_staged", "tone_fetch", "tone_sync", "tone_host_buffers", "tone_export_state",
+    "tone_stage", "tone_step_staged", "tone_fetch", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
     "tone_import_state", "tone_step_debug", "tone_selftest_gemm",
 )
 
@@ -75,6 +75,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.tone_step_staged.argtypes = [vp, C.c_int32, vp]
     lib.tone_fetch.argtypes = [vp, C.c_int32, f32p, i32p]
     lib.tone_sync.argtypes = [vp]
+    lib.tone_step_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.tone_host_buffers.argtypes = [vp, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f32p), C.POINTER(i32p)]
     lib.tone_export_state.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
     lib.tone_import_state.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
@@ -206,6 +207,13 @@ class Engine:
 
     def step_staged(self, B: int, cuda_stream: int = 0) -> None:
         self._ck(self._lib.tone_step_staged(self._h, B, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def step_device(self, B: int, d_slots: int, d_pcm: int, d_logprobs: int = 0, d_tokens: int = 0,
+                    cuda_stream: int = 0) -> None:
+        """Asynchronous step on raw device pointers (e.g. torch tensors' data_ptr())."""
+        vp = C.c_void_p
+        self._ck(self._lib.tone_step_device(self._h, B, vp(d_slots or None), vp(d_pcm or None),
+                                            vp(d_logprobs or None), vp(d_tokens or None), vp(cuda_stream or None)))
 
     def fetch(self, B: int, tokens: bool = True):
         self._ck(self._lib.tone_fetch(self._h, B, _f32p(self.h_logprobs), _i32p(self.h_tokens) if tokens else None))
