@@ -13,8 +13,9 @@ namespace tone {
 typedef __nv_bfloat16 bf16;
 
 // ----------------------------------------------------------------------------- math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// x * sigmoid(x) and sigmoid(x) with the approximate reciprocal (2 ulp; the results are rounded to bf16 anyway)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -42,6 +43,7 @@ struct ProfRec {
   long long id;                   // kernel id: GEMM = 1000 + 100*KIND + BN/8 ; others 1..6
   long long grid;                 // number of CTAs
 };
+__shared__ int prof_seq_s;
 __device__ ProfRec* g_prof = nullptr;
 __device__ unsigned int g_prof_n = 0;
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -49,7 +51,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define PROF_DECL() __shared__ int prof_seq_s
+#define PROF_DECL()
 #define PROF_BEGIN(kid)                                                          \
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_prof) {        \
     prof_seq_s = (int)atomicAdd(&g_prof_n, 1u);                                  \
@@ -195,6 +197,52 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Asynchronous TMEM loads: issue several, then tmem_ld_wait(), then TMEM_REGS_READY on every destination array so
+// that no consumer of those registers can be scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_regs_ready16(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// Load NCOLS (multiple of 16) consecutive accumulator columns of this thread's TMEM lane.
+template <int NCOLS>
+__device__ __forceinline__ void tmem_load_row(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 16) tmem_ld16_async(taddr + c, r + c);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 16) tmem_regs_ready16(r + c);
+}
+
+// Shared-memory accesses through 32-bit shared-window addresses (generic pointers would compile to LD.E / ST.E).
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms 1024 B apart).

@@ -133,7 +133,8 @@ struct tone_engine {
   // step scratch
   int rows_alloc;
   int *d_slots, *d_pcm, *d_len_in, *d_tokens;
-  float *r_full, *r_red, *qkv, *P, *logprobs;
+  float *r_full, *r_red, *qkv, *P, *logprobs, *part;
+  int max_splits = 8;
   bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
   CUtensorMap m_feat, m_x1, m_kv14, m_kv15, m_n, m_h, m_ctx, m_e, m_c1, m_mred;
   CUtensorMap w_feat, w_x1, w_kv14, w_kv15;   // same views with a box spanning the G slots of one tile
@@ -231,7 +232,7 @@ static std::vector<float> concat(std::initializer_list<const std::vector<float>*
 }
 
 // ------------------------------------------------------------------------------------------------ create / destroy
-static const int BN_SWIGLU = 128, BN_RESID = 32, BN_GLU = 64, BN_STORE = 64, BN_CONV = 128, BN_KV = 64;
+static const int BN_SWIGLU = 128, BN_RESID = 32, BN_GLU = 64, BN_STORE = 64, BN_CONV = 128, BN_KV = 64, BN_PART = 128;
 
 extern "C" const char* tone_last_error(void) { return g_err; }
 
@@ -297,6 +298,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   rc |= dev_alloc(e, &e->qkv, std::max(R * 3 * D_MODEL, Bm * (MHSA_S + MAX_T) * 2 * D_MODEL + R * D_MODEL));
   rc |= dev_alloc(e, &e->P, Bm * N_HEADS * MAX_T * (MHSA_S + MAX_T));
   rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
+  rc |= dev_alloc(e, &e->part, (size_t)e->max_splits * R * D_MODEL);
   rc |= dev_alloc(e, &e->n, R * D_MODEL);
   rc |= dev_alloc(e, &e->h, R * D_FF);
   rc |= dev_alloc(e, &e->ctx, R * D_MODEL);
@@ -350,6 +352,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_CONV1, BN_CONV>()));
   CK((configure_gemm_tc<G_KV, BN_KV>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
+  CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
@@ -585,7 +588,7 @@ static int finalize_layer(tone_engine* e, int l) {
     WeightMat* md = k == 0 ? &L.ff1_down : &L.ff2_down;
     if ((rc = upload_mat(e, up, 2 * D_FF, D_MODEL, BN_SWIGLU, mu))) return rc;
     if ((rc = upload_f32(e, upb, k == 0 ? &L.ff1_up_b : &L.ff2_up_b))) return rc;
-    if ((rc = upload_mat(e, w2->data, D_MODEL, D_FF, BN_RESID, md))) return rc;
+    if ((rc = upload_mat(e, w2->data, D_MODEL, D_FF, BN_PART, md))) return rc;
     if ((rc = upload_f32(e, b2->data, k == 0 ? &L.ff1_down_b : &L.ff2_down_b))) return rc;
   }
   const std::string A = Lp + "self_attn.";
@@ -734,13 +737,13 @@ extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slot
 // ------------------------------------------------------------------------------------------------ the step
 template <int KIND, int BN>
 static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const WeightMat& w, GemmArgs a, int m_tiles,
-                int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr) {
+                int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr, int splits = 1) {
   a.W = w.ptr;
   a.ldw = w.K;
   cudaError_t err;
   if (e->cfg.gemm_impl == 0)
-    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, w.map, a, m_tiles, n_tiles, e->pdl, e->num_sms);
-  else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols);
+    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, w.map, a, m_tiles, n_tiles, e->pdl, e->num_sms, splits);
+  else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols, splits);
   e->launches++;
   if (err != cudaSuccess) return fail(TONE_ECUDA, "gemm kind %d launch: %s", KIND, cudaGetErrorString(err));
   return 0;
@@ -774,20 +777,40 @@ static GemmArgs dense_args(int M, int K, const bf16* A, void* out, int ldo, cons
     if (_e != cudaSuccess) return fail(TONE_ECUDA, "launch at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
   } while (0)
 
+struct PartIn {            // split-K output waiting to be folded into the residual stream by the next norm kernel
+  const float* part = nullptr;
+  int nsplit = 0;
+  long long stride = 0;
+  const float* bias = nullptr;
+  float scale = 0.f;
+};
+
 static int run_norm(tone_engine* e, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
-                    bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
-  NormArgs a{r, g1, g2, n, M, kv, e->d_slots, rows_per_stream, kv_row_off};
+                    const PartIn& p = PartIn(), bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
+  NormArgs a{r, g1, g2, n, M, p.part, p.nsplit, p.stride, p.bias, p.scale, kv, e->d_slots, rows_per_stream, kv_row_off};
   KLAUNCH(launch_kernel(norm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
   return 0;
 }
 
-static int run_ff(tone_engine* e, cudaStream_t st, int M, float* r, const WeightMat& up, const float* up_b,
-                  const WeightMat& down, const float* down_b) {
+// Feed-forward: h = silu(n W1^T + b1) * (n Wv^T + bv); the down projection runs split-K and leaves its partial
+// sums in e->part; the NEXT norm kernel adds 0.5 * (sum + b2) to the residual stream (conformer_blocks.py:814,834).
+static int run_ff(tone_engine* e, cudaStream_t st, int M, const WeightMat& up, const float* up_b, const WeightMat& down,
+                  const float* down_b, PartIn* out) {
   const int mt = (M + 127) / 128;
   GemmArgs a = dense_args(M, D_MODEL, e->n, e->h, D_FF, up_b, 1.f);
   RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, e->m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
-  GemmArgs b = dense_args(M, D_FF, e->h, r, D_MODEL, down_b, 0.5f);
-  RC((gemm<G_RESID, BN_RESID>(e, st, e->m_h, down, b, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+  int splits = 1;
+  while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
+  if (const char* v = getenv("TONE_SPLITK")) splits = atoi(v);
+  GemmArgs b = dense_args(M, D_FF / splits, e->h, e->part, D_MODEL, nullptr, 1.f);
+  b.lda = D_FF;
+  b.z_stride = (long long)e->rows_alloc * D_MODEL;
+  RC((gemm<G_PARTIAL, BN_PART>(e, st, e->m_h, down, b, mt, D_MODEL / BN_PART, M, D_MODEL, nullptr, splits)));
+  out->part = e->part;
+  out->nsplit = splits;
+  out->stride = b.z_stride;
+  out->bias = down_b;
+  out->scale = 0.5f;
   return 0;
 }
 
@@ -876,8 +899,9 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     float* r = reduced ? e->r_red : e->r_full;
     M = B * Tl;
     const int mt = (M + 127) / 128;
-    RC(run_ff(e, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b));
-    // ---- attention
+    PartIn ff;
+    RC(run_ff(e, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
+    // ---- attention (its norm kernel first folds the feed-forward output into r)
     AttnArgs at;
     memset(&at, 0, sizeof(at));
     at.P = e->P;
@@ -888,7 +912,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     at.T = Tl;
     at.recompute = RECOMPUTE[l] ? 1 : 0;
     if (l < 14) {
-      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M));
+      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
@@ -911,7 +935,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     } else {
       const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
       bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
-      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, kvbuf, Tl, S));
+      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, ff, kvbuf, Tl, S));
       float* qbuf = e->qkv;
       float* kvout = e->qkv + (size_t)e->rows_alloc * D_MODEL;
       GemmArgs a = dense_args(M, D_MODEL, e->n, qbuf, D_MODEL, L.q_b, 1.f);
@@ -973,9 +997,9 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     }
     // ---- second feed-forward, norm_out and what follows the layer
     RC(run_norm(e, st, r, nullptr, L.n_ff2, e->n, M));
-    RC(run_ff(e, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b));
+    RC(run_ff(e, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff));
     if (l == 6) {
-      RC(run_norm(e, st, r, L.n_out, nullptr, nullptr, M));   // r_full = layer output = residual kept for layer 14
+      RC(run_norm(e, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{e->r_full, e->st_red, e->d_slots, e->red_dw_w, e->red_dw_b, e->m_red, T, T2};
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
@@ -984,14 +1008,15 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
       RC(run_norm(e, st, e->r_red, nullptr, e->L[7].n_ff1, e->n, M2));
       RC(tap(1 + l, e->r_red, M2));
     } else if (l == 14) {
-      UpsampleArgs ua{e->r_full, e->r_red, L.n_out, e->L[15].n_ff1, e->n, B, T, T2};
+      UpsampleArgs ua{e->r_full, e->r_red, ff.part, ff.nsplit, ff.stride, ff.bias, ff.scale,
+                      L.n_out, e->L[15].n_ff1, e->n, B, T, T2};
       KLAUNCH(launch_kernel(upsample_norm_kernel, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, e->r_full, B * T));
     } else if (l == 15) {
-      RC(run_norm(e, st, r, L.n_out, nullptr, e->n, M));
+      RC(run_norm(e, st, r, L.n_out, nullptr, e->n, M, ff));
       RC(tap(1 + l, r, M));
     } else {
-      RC(run_norm(e, st, r, L.n_out, e->L[l + 1].n_ff1, e->n, M));
+      RC(run_norm(e, st, r, L.n_out, e->L[l + 1].n_ff1, e->n, M, ff));
       RC(tap(1 + l, r, M));
     }
   }

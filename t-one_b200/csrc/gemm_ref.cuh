@@ -57,7 +57,15 @@ __global__ void gemm_ref_kernel(const GemmArgs a, int n_out) {
     b = row / a.R;
     j = row - b * a.R;
   }
-  if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
+  if constexpr (KIND == G_PARTIAL) {
+    // K slice z: a.nk iterations of 64 starting at z * a.nk * 64
+    const int z = blockIdx.z, klen = a.nk * 64;
+    const bf16* ar = a.A + (long long)row * a.lda + (long long)z * klen;
+    const bf16* w = a.W + (long long)col * a.ldw + (long long)z * klen;
+    float acc = 0.f;
+    for (int k = 0; k < klen; ++k) acc += __bfloat162float(ar[k]) * __bfloat162float(w[k]);
+    reinterpret_cast<float*>(a.out)[z * a.z_stride + (long long)row * a.ldo + col] = acc;
+  } else if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
     float v = ref_dot<KIND>(a, b, j, 0, col) + (a.bias ? a.bias[col] : 0.f);
     reinterpret_cast<float*>(a.out)[(long long)row * a.ldo + col] = v;
   } else if constexpr (KIND == G_RESID) {
@@ -108,11 +116,11 @@ __global__ void decoder_ref_kernel(const GemmArgs a) {
 }
 
 template <int KIND, int BN>
-inline cudaError_t launch_gemm_ref(cudaStream_t st, const GemmArgs& a, int rows, int n_out) {
+inline cudaError_t launch_gemm_ref(cudaStream_t st, const GemmArgs& a, int rows, int n_out, int splits = 1) {
   if constexpr (KIND == G_DECODER) {
     decoder_ref_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a);
   } else {
-    gemm_ref_kernel<KIND, BN><<<dim3(rows, (n_out + 127) / 128), 128, 0, st>>>(a, n_out);
+    gemm_ref_kernel<KIND, BN><<<dim3(rows, (n_out + 127) / 128, splits), 128, 0, st>>>(a, n_out);
   }
   return cudaGetLastError();
 }

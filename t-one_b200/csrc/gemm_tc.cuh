@@ -25,6 +25,7 @@ enum GemmKind : int {
   G_CONV1 = 5,      // c1 bf16 = silu(acc*alpha + beta)                      (gather A from x1 windows)
   G_KV = 6,         // out fp32 = acc + bias, gather A from [cache|new] rows (layers 14, 15)
   G_DECODER = 7,    // logprobs = log_softmax(acc + bias)[0:35], argmax      (BN = 48)
+  G_PARTIAL = 8,    // part[z] fp32 = acc over K slice z (split-K; blockIdx.z)  (ff down; summed by addnorm_kernel)
 };
 
 struct GemmArgs {
@@ -41,6 +42,7 @@ struct GemmArgs {
   long long out_slot_stride;  // G_CONV0: elements between consecutive slots of x1
   int out_row_off;            // G_CONV0: first row written inside a slot (the cached rows come first)
   int* tokens;                // G_DECODER
+  long long z_stride;         // G_PARTIAL: elements between the partial outputs of consecutive K slices
   // Raw operand views, used only by the SIMT debug kernels (gemm_ref.cuh); the tensor-core path reads through
   // the tensor maps.
   const bf16* A;
@@ -100,7 +102,9 @@ __device__ __forceinline__ RowInfo row_info(const GemmArgs& a, int row_in_tile) 
 template <int KIND, int BN>
 __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..127*/) {
   const int n0 = blockIdx.y * BN;
-  if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
+  if constexpr (KIND == G_PARTIAL) {
+    return;
+  } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
     constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
     if (t < BN) {
       s_c0[t] = __ldg(a.alpha + (n0 + t) % CH);
@@ -113,108 +117,45 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
   }
 }
 
+// Output geometry of one tile row, in bytes of the FINAL output type.
 template <int KIND, int BN>
-__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int row_in_tile,
+struct OutCfg {
+  static constexpr bool f32 = (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_PARTIAL || KIND == G_RESID);
+  static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU) ? BN : BN * 2);
+  static constexpr int STRIDE = ROW_BYTES + 16;   // +16 B: float4 stores of a quarter-warp hit distinct banks
+  static constexpr int LPR = ROW_BYTES / 16;      // lanes per output row in the coalesced phase
+  static constexpr int RPI = 32 / LPR;            // rows per warp instruction
+};
+
+template <int KIND>
+__device__ __forceinline__ char* out_row_ptr(const GemmArgs& a, const RowInfo& ri, int n0_elems) {
+  if constexpr (KIND == G_PARTIAL)
+    return reinterpret_cast<char*>(reinterpret_cast<float*>(a.out) + blockIdx.z * a.z_stride + ri.out_row * a.ldo + n0_elems);
+  else if constexpr (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_RESID)
+    return reinterpret_cast<char*>(reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0_elems);
+  else if constexpr (KIND == G_CONV0)
+    return reinterpret_cast<char*>(reinterpret_cast<bf16*>(a.out) + ri.out_row + n0_elems);
+  else
+    return reinterpret_cast<char*>(reinterpret_cast<bf16*>(a.out) + ri.out_row * (long long)a.ldo + n0_elems);
+}
+
+// Epilogue of one warp (TMEM lanes / tile rows 32q .. 32q+31), two phases:
+//  1. each thread owns one accumulator row: tcgen05.ld 16 columns at a time, apply the column-wise math (bias,
+//     activation, gating, folded BatchNorm), and park the result in shared memory in its final element type;
+//  2. the warp writes its 32 rows back out with lanes running along the row, so every global store (and the
+//     residual read of G_RESID) is a contiguous 16 B-per-lane access.
+// The staging area is the operand ring, which is idle once the accumulator barrier has fired.
+template <int KIND, int BN>
+__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int q, int lane, char* stage,
                                          const float* s_c0, const float* s_c1, uint64_t* tmem_full) {
-  const RowInfo ri = row_info<KIND>(a, row_in_tile);
+  using O = OutCfg<KIND, BN>;
   const int n0 = blockIdx.y * BN;
-  float v[16];
-  if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
-    float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < BN; c += 16) {
-      tmem_ld16(tmem_row_base + c, v);
-      if (ri.valid) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(out + c + i) = make_float4(v[i] + s_c0[c + i], v[i + 1] + s_c0[c + i + 1],
-                                                                v[i + 2] + s_c0[c + i + 2], v[i + 3] + s_c0[c + i + 3]);
-      }
-    }
-  } else if constexpr (KIND == G_RESID) {
-    // the residual row segment is fetched while the main loop runs
-    float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0;
-    float4 r[BN / 4];
-    if (ri.valid) {
-#pragma unroll
-      for (int i = 0; i < BN / 4; ++i) r[i] = *reinterpret_cast<const float4*>(out + 4 * i);
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < BN; c += 16) {
-      tmem_ld16(tmem_row_base + c, v);
-      if (ri.valid) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 o = r[(c + i) / 4];
-          o.x += a.scale * (v[i + 0] + s_c0[c + i + 0]);
-          o.y += a.scale * (v[i + 1] + s_c0[c + i + 1]);
-          o.z += a.scale * (v[i + 2] + s_c0[c + i + 2]);
-          o.w += a.scale * (v[i + 3] + s_c0[c + i + 3]);
-          *reinterpret_cast<float4*>(out + c + i) = o;
-        }
-      }
-    }
-  } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
-    constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
-    bf16* __restrict__ out = reinterpret_cast<bf16*>(a.out) + ri.out_row * a.ldo + blockIdx.y * HW;
-    float w[16];
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < HW; c += 16) {
-      tmem_ld16(tmem_row_base + c, v);
-      tmem_ld16(tmem_row_base + HW + c, w);
-      if (ri.valid) {
-        uint32_t p[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float x0 = v[i] + s_c0[c + i], x1 = v[i + 1] + s_c0[c + i + 1];
-          float y0 = w[i] + s_c0[HW + c + i], y1 = w[i + 1] + s_c0[HW + c + i + 1];
-          float r0, r1;
-          if constexpr (KIND == G_SWIGLU) {
-            r0 = silu_f(x0) * y0;
-            r1 = silu_f(x1) * y1;
-          } else {
-            r0 = x0 * sigmoid_f(y0);
-            r1 = x1 * sigmoid_f(y1);
-          }
-          p[i / 2] = pack_bf16x2(r0, r1);
-        }
-        uint4* o = reinterpret_cast<uint4*>(out + c);
-        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-      }
-    }
-  } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
-    // column n of conv0 is (f = n/32, o = n%32); tile column c of conv1 is (j = c/64, o = c%64)
-    bf16* __restrict__ out = reinterpret_cast<bf16*>(a.out) +
-                             (KIND == G_CONV0 ? ri.out_row : ri.out_row * (long long)a.ldo) + n0;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < BN; c += 16) {
-      tmem_ld16(tmem_row_base + c, v);
-      if (ri.valid) {
-        uint32_t p[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float r0 = silu_f(v[i] * s_c0[c + i] + s_c1[c + i]);
-          float r1 = silu_f(v[i + 1] * s_c0[c + i + 1] + s_c1[c + i + 1]);
-          p[i / 2] = pack_bf16x2(r0, r1);
-        }
-        uint4* o = reinterpret_cast<uint4*>(out + c);
-        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-      }
-    }
-  } else if constexpr (KIND == G_DECODER) {
-    static_assert(KIND != G_DECODER || BN == 48, "decoder tile is 48 columns (35 classes + padding)");
+
+  if constexpr (KIND == G_DECODER) {
+    const RowInfo ri = row_info<KIND>(a, q * 32 + lane);
     float lg[48];
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
     tmem_ld16(tmem_row_base + 0, lg);
     tmem_ld16(tmem_row_base + 16, lg + 16);
@@ -238,6 +179,101 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 #pragma unroll
       for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
       if (a.tokens) a.tokens[ri.out_row] = am;
+    }
+    return;
+  } else {
+    // element offset of this tile's first output column
+    const int n0_out = (KIND == G_SWIGLU || KIND == G_GLU) ? blockIdx.y * (BN / 2) : n0;
+    // phase-2 geometry (also used to prefetch the residual before the accumulator is ready)
+    const int sub_row = lane / O::LPR, cb = (lane % O::LPR) * 16;
+    float4 rres[32 / O::RPI];
+    if constexpr (KIND == G_RESID) {
+#pragma unroll
+      for (int it = 0; it < 32 / O::RPI; ++it) {
+        const RowInfo ri = row_info<KIND>(a, q * 32 + it * O::RPI + sub_row);
+        if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) PROF_MARK(4);
+    tc_fence_after();
+
+    // ---- phase 1: accumulator row -> final-type row in shared memory (all TMEM loads in flight, one wait)
+    float acc[BN];
+    tmem_load_row<BN>(tmem_row_base, acc);
+    const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
+    const uint32_t c0a = smem_u32(s_c0), c1a = smem_u32(s_c1);
+    if constexpr (O::f32) {
+#pragma unroll
+      for (int c = 0; c < BN; c += 4) {
+        float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if constexpr (KIND != G_PARTIAL) {
+          const float4 bb = lds128(c0a + c * 4);
+          o.x += bb.x;
+          o.y += bb.y;
+          o.z += bb.z;
+          o.w += bb.w;
+        }
+        if constexpr (KIND == G_RESID) {
+          o.x *= a.scale;
+          o.y *= a.scale;
+          o.z *= a.scale;
+          o.w *= a.scale;
+        }
+        sts128(srow + c * 4, o);
+      }
+    } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
+      constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
+#pragma unroll
+      for (int c = 0; c < HW; c += 8) {
+        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
+        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = acc[c + i] + gb[i], y = acc[HW + c + i] + ub[i];
+          r[i] = (KIND == G_SWIGLU) ? silu_f(x) * y : x * sigmoid_f(y);
+        }
+        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                         pack_bf16x2(r[6], r[7])));
+      }
+    } else {  // G_CONV0 / G_CONV1: folded BatchNorm + SiLU per output channel
+#pragma unroll
+      for (int c = 0; c < BN; c += 8) {
+        const float4 a0 = lds128(c0a + c * 4), a1 = lds128(c0a + c * 4 + 16);
+        const float4 b0 = lds128(c1a + c * 4), b1 = lds128(c1a + c * 4 + 16);
+        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = silu_f(acc[c + i] * al[i] + be[i]);
+        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                         pack_bf16x2(r[6], r[7])));
+      }
+    }
+    __syncwarp();
+
+    // ---- phase 2: coalesced write-out of this warp's 32 rows
+#pragma unroll
+    for (int it = 0; it < 32 / O::RPI; ++it) {
+      const int row = q * 32 + it * O::RPI + sub_row;
+      const RowInfo ri = row_info<KIND>(a, row);
+      if (ri.valid) {
+        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
+        if constexpr (KIND == G_RESID) {
+          const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
+          float4 o = rres[it];
+          o.x += d.x;
+          o.y += d.y;
+          o.z += d.z;
+          o.w += d.w;
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
+        }
+      }
     }
   }
 }
@@ -293,12 +329,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
       const uint32_t a_bytes = KindTraits<KIND>::gather ? (uint32_t)(nvalid * a.R * 128) : (uint32_t)Cfg::A_BYTES;
       const int b_row = (KIND == G_CONV1) ? 0 : blockIdx.y * BN;
+      const int kz = (KIND == G_PARTIAL) ? blockIdx.z * a.nk * 64 : 0;   // first K element of this CTA's slice
       // The weight tiles do not depend on the previous kernel: put the first ring of them in flight, then wait for
       // the predecessor grid before touching activations.
       const int npre = a.nk < STAGES ? a.nk : STAGES;
       for (int it = 0; it < npre; ++it) {
         mbar_expect_tx(&full[it], a_bytes + Cfg::B_BYTES);
-        tma_load_2d(sB + it * Cfg::B_BYTES, &tmB, &full[it], it * 64, b_row);
+        tma_load_2d(sB + it * Cfg::B_BYTES, &tmB, &full[it], kz + it * 64, b_row);
       }
       pdl_wait();
       PROF_MARK(2);                     // predecessor grid complete
@@ -317,7 +354,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (it >= npre) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
-          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], it * 64, b_row);
+          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], kz + it * 64, b_row);
         }
         uint8_t* dA = sA + s * Cfg::A_BYTES;
         if constexpr (KIND == G_CONV0) {
@@ -342,7 +379,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             for (int g = 0; g < nvalid; ++g)
               tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
         } else {
-          tma_load_2d(dA, &tmA, &full[s], it * 64, blockIdx.x * 128);
+          tma_load_2d(dA, &tmA, &full[s], kz + it * 64, blockIdx.x * 128);
         }
       }
     }
@@ -371,8 +408,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     stage_constants<KIND, BN>(a, s_c0, s_c1, threadIdx.x - 64);
     asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
     pdl_wait();
-    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q * 32 + lane, s_c0, s_c1, tmem_full);
-    if (threadIdx.x == 64) PROF_MARK(4);
+    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q, lane, reinterpret_cast<char*>(sA), s_c0,
+                       s_c1, tmem_full);
   }
   tc_fence_before();
   __syncthreads();
@@ -412,9 +449,9 @@ inline cudaError_t configure_gemm_tc() {
 template <int KIND, int BN>
 inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmAw,
                                   const CUtensorMap& tmB, const GemmArgs& a, int m_tiles, int n_tiles, bool pdl,
-                                  int num_sms) {
-  const dim3 grid(m_tiles, n_tiles);
-  if (m_tiles * n_tiles <= 2 * num_sms)
+                                  int num_sms, int splits = 1) {
+  const dim3 grid(m_tiles, n_tiles, splits);
+  if (m_tiles * n_tiles * splits <= 2 * num_sms)
     return launch_kernel(gemm_tc_kernel<KIND, BN, true>, grid, dim3(192), TileCfg<BN, true>::SMEM_BYTES, st, pdl, tmA,
                          tmAw, tmB, a);
   return launch_kernel(gemm_tc_kernel<KIND, BN, false>, grid, dim3(192), TileCfg<BN, false>::SMEM_BYTES, st, pdl, tmA,

@@ -204,6 +204,12 @@ struct NormArgs {
   const float* g2;
   bf16* n;
   int M;
+  // optional split-K input: x = r + scale * (sum_z part[z][row] + bias) is formed (and written back to r) first
+  const float* part;
+  int nsplit;
+  long long part_stride;
+  const float* bias;
+  float scale;
   bf16* kv;            // nullable
   const int* slots;
   int rows_per_stream; // T of this layer
@@ -229,6 +235,26 @@ __device__ __forceinline__ void scale_384(float4 (&x)[3], const float* g, float 
   }
 }
 
+// x += scale * (sum_z part[z] + bias): fixed summation order, so split-K stays deterministic.
+__device__ __forceinline__ void add_partials_384(float4 (&x)[3], const float* part_row, int nsplit, long long stride,
+                                                 const float* bias, float scale, int lane) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float4 s = *reinterpret_cast<const float4*>(bias + i * 128 + lane * 4);
+    for (int z = 0; z < nsplit; ++z) {
+      const float4 p = *reinterpret_cast<const float4*>(part_row + z * stride + i * 128 + lane * 4);
+      s.x += p.x;
+      s.y += p.y;
+      s.z += p.z;
+      s.w += p.w;
+    }
+    x[i].x += scale * s.x;
+    x[i].y += scale * s.y;
+    x[i].z += scale * s.z;
+    x[i].w += scale * s.w;
+  }
+}
+
 __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
   PROF_DECL();
   PROF_BEGIN(2);
@@ -242,8 +268,9 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
   float4 x[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rr + i * 128 + lane * 4);
-  if (a.g1) {
-    scale_384(x, a.g1, rms_inv_384(x), lane);
+  if (a.part) add_partials_384(x, a.part + (size_t)row * D_MODEL, a.nsplit, a.part_stride, a.bias, a.scale, lane);
+  if (a.g1) scale_384(x, a.g1, rms_inv_384(x), lane);
+  if (a.part || a.g1) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = x[i];
   }
@@ -270,6 +297,11 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
 struct UpsampleArgs {
   float* r_full;
   const float* r_red;
+  const float* part;      // split-K output of layer 14's second feed-forward (added to r_red rows first)
+  int nsplit;
+  long long part_stride;
+  const float* bias;
+  float scale;
   const float* g_out;   // norm_out of layer 14
   const float* g_next;  // norm_feed_forward1 of layer 15
   bf16* n;
@@ -294,6 +326,9 @@ __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a
     const float* rs = a.r_red + ((size_t)b * a.T2 + (t >> 1)) * D_MODEL;
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rs + i * 128 + lane * 4);
+    if (a.part)
+      add_partials_384(x, a.part + ((size_t)b * a.T2 + (t >> 1)) * D_MODEL, a.nsplit, a.part_stride, a.bias, a.scale,
+                       lane);
     scale_384(x, a.g_out, rms_inv_384(x), lane);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
