@@ -130,14 +130,31 @@ struct tone_engine {
   std::vector<int> free_slots;
   std::vector<char> slot_used;
 
-  // step scratch
+  // step inputs / outputs (batch order)
   int rows_alloc;
   int *d_slots, *d_pcm, *d_len_in, *d_tokens;
-  float *r_full, *r_red, *qkv, *P, *logprobs, *part;
+  float* logprobs;
   int max_splits = 8;
-  bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
-  CUtensorMap m_feat, m_x1, m_kv14, m_kv15, m_n, m_h, m_ctx, m_e, m_c1, m_mred;
+  CUtensorMap m_feat, m_x1, m_kv14, m_kv15;
   CUtensorMap w_feat, w_x1, w_kv14, w_kv15;   // same views with a box spanning the G slots of one tile
+  // The batch is cut into up to n_lanes independent sub-batches whose kernel chains run concurrently (fork/join in
+  // the captured graph): at small batch the step is bound by kernel-to-kernel latency, not by the SMs.
+  struct Lane {
+    float *r_full, *r_red, *qkv, *P, *part;
+    bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
+    CUtensorMap m_n, m_h, m_ctx, m_e, m_c1, m_mred;
+    cudaStream_t stream = nullptr;       // lanes > 0 run on their own stream between fork and join
+    cudaEvent_t done = nullptr;
+    // view of the sub-batch this lane is working on (set per step)
+    const int* slots;
+    const int* pcm;
+    int* len_in;
+    float* lp_out;
+    int* tok_out;
+  };
+  std::vector<Lane> lanes;
+  int n_lanes = 2, lane_min_batch = 256;   // measured: lanes only pay once kernels are throughput bound (B >= 512)
+  cudaEvent_t fork_ev = nullptr;
 
   // pinned staging
   int *p_slots, *p_pcm, *p_tokens;
@@ -293,19 +310,31 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   rc |= dev_alloc(e, &e->d_pcm, Bm * e->C);
   rc |= dev_alloc(e, &e->d_len_in, Bm);
   rc |= dev_alloc(e, &e->d_tokens, R);
-  rc |= dev_alloc(e, &e->r_full, R * D_MODEL);
-  rc |= dev_alloc(e, &e->r_red, R * D_MODEL);
-  rc |= dev_alloc(e, &e->qkv, std::max(R * 3 * D_MODEL, Bm * (MHSA_S + MAX_T) * 2 * D_MODEL + R * D_MODEL));
-  rc |= dev_alloc(e, &e->P, Bm * N_HEADS * MAX_T * (MHSA_S + MAX_T));
   rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
-  rc |= dev_alloc(e, &e->part, (size_t)e->max_splits * R * D_MODEL);
-  rc |= dev_alloc(e, &e->n, R * D_MODEL);
-  rc |= dev_alloc(e, &e->h, R * D_FF);
-  rc |= dev_alloc(e, &e->ctx, R * D_MODEL);
-  rc |= dev_alloc(e, &e->g, R * D_MODEL);
-  rc |= dev_alloc(e, &e->ebuf, R * D_MODEL);
-  rc |= dev_alloc(e, &e->c1, R * SUB_OUT);
-  rc |= dev_alloc(e, &e->m_red, R * D_FF);
+  if (const char* v = getenv("TONE_LANES")) e->n_lanes = std::max(1, std::min(8, atoi(v)));
+  if (const char* v = getenv("TONE_LANE_MIN_BATCH")) e->lane_min_batch = std::max(1, atoi(v));
+  e->lanes.resize(e->n_lanes);
+  for (int li = 0; li < e->n_lanes; ++li) {
+    tone_engine::Lane& ln = e->lanes[li];
+    rc |= dev_alloc(e, &ln.r_full, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.r_red, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.qkv, std::max(R * 3 * D_MODEL, Bm * (MHSA_S + MAX_T) * 2 * D_MODEL + R * D_MODEL));
+    rc |= dev_alloc(e, &ln.P, Bm * N_HEADS * MAX_T * (MHSA_S + MAX_T));
+    rc |= dev_alloc(e, &ln.part, (size_t)e->max_splits * R * D_MODEL);
+    rc |= dev_alloc(e, &ln.n, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.h, R * D_FF);
+    rc |= dev_alloc(e, &ln.ctx, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.g, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.ebuf, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.c1, R * SUB_OUT);
+    rc |= dev_alloc(e, &ln.m_red, R * D_FF);
+    if (rc) return rc;
+    if (li > 0) {
+      CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+  }
+  CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
   if (rc) return rc;
   CK(cudaMallocHost((void**)&e->p_slots, Bm * 4));
   CK(cudaMallocHost((void**)&e->p_pcm, Bm * e->C * 4));
@@ -335,12 +364,14 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
     if ((rc = make_map(e, &e->w_kv14, e->st_kv14, 3, d, s, w14, false))) return rc;
     if ((rc = make_map(e, &e->w_kv15, e->st_kv15, 3, d, s, w15, false))) return rc;
   }
-  if ((rc = make_map_2d(e, &e->m_n, e->n, R, D_MODEL, 128, false))) return rc;
-  if ((rc = make_map_2d(e, &e->m_h, e->h, R, D_FF, 128, false))) return rc;
-  if ((rc = make_map_2d(e, &e->m_ctx, e->ctx, R, D_MODEL, 128, false))) return rc;
-  if ((rc = make_map_2d(e, &e->m_e, e->ebuf, R, D_MODEL, 128, false))) return rc;
-  if ((rc = make_map_2d(e, &e->m_c1, e->c1, R, SUB_OUT, 128, false))) return rc;
-  if ((rc = make_map_2d(e, &e->m_mred, e->m_red, R, D_FF, 128, false))) return rc;
+  for (auto& ln : e->lanes) {
+    if ((rc = make_map_2d(e, &ln.m_n, ln.n, R, D_MODEL, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_h, ln.h, R, D_FF, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_ctx, ln.ctx, R, D_MODEL, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_e, ln.ebuf, R, D_MODEL, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_c1, ln.c1, R, SUB_OUT, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_mred, ln.m_red, R, D_FF, 128, false))) return rc;
+  }
 
   CK((configure_gemm_tc<G_SWIGLU, BN_SWIGLU>()));
   CK((configure_gemm_tc<G_RESID, BN_RESID>()));
@@ -364,6 +395,11 @@ extern "C" void tone_destroy(tone_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& ln : e->lanes) {
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+    if (ln.done) cudaEventDestroy(ln.done);
+  }
+  if (e->fork_ev) cudaEventDestroy(e->fork_ev);
   for (void* p : e->allocs) cudaFree(p);
   cudaFree(e->w_arena);
   cudaFreeHost(e->p_slots);
@@ -785,28 +821,28 @@ struct PartIn {            // split-K output waiting to be folded into the resid
   float scale = 0.f;
 };
 
-static int run_norm(tone_engine* e, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
+static int run_norm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
                     const PartIn& p = PartIn(), bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
-  NormArgs a{r, g1, g2, n, M, p.part, p.nsplit, p.stride, p.bias, p.scale, kv, e->d_slots, rows_per_stream, kv_row_off};
+  NormArgs a{r, g1, g2, n, M, p.part, p.nsplit, p.stride, p.bias, p.scale, kv, ln.slots, rows_per_stream, kv_row_off};
   KLAUNCH(launch_kernel(norm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
   return 0;
 }
 
 // Feed-forward: h = silu(n W1^T + b1) * (n Wv^T + bv); the down projection runs split-K and leaves its partial
-// sums in e->part; the NEXT norm kernel adds 0.5 * (sum + b2) to the residual stream (conformer_blocks.py:814,834).
-static int run_ff(tone_engine* e, cudaStream_t st, int M, const WeightMat& up, const float* up_b, const WeightMat& down,
+// sums in ln.part; the NEXT norm kernel adds 0.5 * (sum + b2) to the residual stream (conformer_blocks.py:814,834).
+static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const WeightMat& up, const float* up_b, const WeightMat& down,
                   const float* down_b, PartIn* out) {
   const int mt = (M + 127) / 128;
-  GemmArgs a = dense_args(M, D_MODEL, e->n, e->h, D_FF, up_b, 1.f);
-  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, e->m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+  GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.h, D_FF, up_b, 1.f);
+  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ln.m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
   int splits = 1;
   while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
   if (const char* v = getenv("TONE_SPLITK")) splits = atoi(v);
-  GemmArgs b = dense_args(M, D_FF / splits, e->h, e->part, D_MODEL, nullptr, 1.f);
+  GemmArgs b = dense_args(M, D_FF / splits, ln.h, ln.part, D_MODEL, nullptr, 1.f);
   b.lda = D_FF;
   b.z_stride = (long long)e->rows_alloc * D_MODEL;
-  RC((gemm<G_PARTIAL, BN_PART>(e, st, e->m_h, down, b, mt, D_MODEL / BN_PART, M, D_MODEL, nullptr, splits)));
-  out->part = e->part;
+  RC((gemm<G_PARTIAL, BN_PART>(e, st, ln.m_h, down, b, mt, D_MODEL / BN_PART, M, D_MODEL, nullptr, splits)));
+  out->part = ln.part;
   out->nsplit = splits;
   out->stride = b.z_stride;
   out->bias = down_b;
@@ -815,9 +851,8 @@ static int run_ff(tone_engine* e, cudaStream_t st, int M, const WeightMat& up, c
 }
 
 // taps: optional host pointer [17][B*T][384]; when set the step synchronises after every layer (debug only)
-static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
+static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t st, float* taps) {
   const int T = e->T, T2 = e->T2, F = e->F, C = e->C;
-  e->launches = 0;
   auto tap = [&](int idx, const float* src, int rows) -> int {
     if (!taps) return 0;
     CK(cudaStreamSynchronize(st));
@@ -827,15 +862,15 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
   {
     BeginArgs a;
     memset(&a, 0, sizeof(a));
-    a.slots = e->d_slots;
-    a.pcm = e->d_pcm;
+    a.slots = ln.slots;
+    a.pcm = ln.pcm;
     a.pre = e->st_pre;
     a.feat = e->st_feat;
     a.x1 = e->st_x1;
     a.kv14 = e->st_kv14;
     a.kv15 = e->st_kv15;
     a.mhsa_len = e->st_len;
-    a.len_in = e->d_len_in;
+    a.len_in = ln.len_in;
     a.basis = e->basis;
     a.mel_start = e->mel_start;
     a.mel_bin = e->mel_bin;
@@ -855,7 +890,7 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     a.nk = 11;
     a.R = F;
     a.G = 128 / F;
-    a.slots = e->d_slots;
+    a.slots = ln.slots;
     a.out = e->st_x1;
     a.ldo = X1_ROW;
     a.alpha = e->conv0_alpha;
@@ -874,8 +909,8 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     a.nk = 66;
     a.R = T;
     a.G = 128 / T;
-    a.slots = e->d_slots;
-    a.out = e->c1;
+    a.slots = ln.slots;
+    a.out = ln.c1;
     a.ldo = SUB_OUT;
     a.alpha = e->conv1_alpha;
     a.beta = e->conv1_beta;
@@ -886,67 +921,67 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
   }
   int M = B * T;
   {
-    GemmArgs a = dense_args(M, SUB_OUT, e->c1, e->r_full, D_MODEL, nullptr, 1.f);
-    RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / BN_STORE, M, D_MODEL)));
+    GemmArgs a = dense_args(M, SUB_OUT, ln.c1, ln.r_full, D_MODEL, nullptr, 1.f);
+    RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / BN_STORE, M, D_MODEL)));
   }
-  RC(run_norm(e, st, e->r_full, e->out_norm_g, e->L[0].n_ff1, e->n, M));
-  RC(tap(0, e->r_full, M));
+  RC(run_norm(e, ln, st, ln.r_full, e->out_norm_g, e->L[0].n_ff1, ln.n, M));
+  RC(tap(0, ln.r_full, M));
 
   for (int l = 0; l < N_LAYERS; ++l) {
     LayerW& L = e->L[l];
     const bool reduced = l > 6 && l <= 14;
     const int Tl = reduced ? T2 : T;
-    float* r = reduced ? e->r_red : e->r_full;
+    float* r = reduced ? ln.r_red : ln.r_full;
     M = B * Tl;
     const int mt = (M + 127) / 128;
     PartIn ff;
-    RC(run_ff(e, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
+    RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
     // ---- attention (its norm kernel first folds the feed-forward output into r)
     AttnArgs at;
     memset(&at, 0, sizeof(at));
-    at.P = e->P;
-    at.ctx = e->ctx;
+    at.P = ln.P;
+    at.ctx = ln.ctx;
     at.rope_cos = e->rope_cos;
     at.rope_sin = e->rope_sin;
-    at.len_in = e->d_len_in;
+    at.len_in = ln.len_in;
     at.T = Tl;
     at.recompute = RECOMPUTE[l] ? 1 : 0;
     if (l < 14) {
-      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, ff));
+      RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
-        GemmArgs a = dense_args(M, D_MODEL, e->n, e->qkv, 3 * D_MODEL, L.qkv_b, 1.f);
-        RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
-        at.q = e->qkv;
-        at.k = e->qkv + D_MODEL;
-        at.v = e->qkv + 2 * D_MODEL;
+        GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, 3 * D_MODEL, L.qkv_b, 1.f);
+        RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
+        at.q = ln.qkv;
+        at.k = ln.qkv + D_MODEL;
+        at.v = ln.qkv + 2 * D_MODEL;
         at.ldq = at.ldk = at.ldv = 3 * D_MODEL;
         at.q_ln_w = L.qln_w;
         at.q_ln_b = L.qln_b;
         at.k_ln_w = L.kln_w;
         at.k_ln_b = L.kln_b;
       } else {
-        GemmArgs a = dense_args(M, D_MODEL, e->n, e->qkv, D_MODEL, L.qkv_b, 1.f);
-        RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.qkv, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
-        at.v = e->qkv;
+        GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, D_MODEL, L.qkv_b, 1.f);
+        RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+        at.v = ln.qkv;
         at.ldv = D_MODEL;
       }
     } else {
       const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
       bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
-      RC(run_norm(e, st, r, nullptr, L.n_att, e->n, M, ff, kvbuf, Tl, S));
-      float* qbuf = e->qkv;
-      float* kvout = e->qkv + (size_t)e->rows_alloc * D_MODEL;
-      GemmArgs a = dense_args(M, D_MODEL, e->n, qbuf, D_MODEL, L.q_b, 1.f);
-      RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_n, L.q, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+      RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
+      float* qbuf = ln.qkv;
+      float* kvout = ln.qkv + (size_t)e->rows_alloc * D_MODEL;
+      GemmArgs a = dense_args(M, D_MODEL, ln.n, qbuf, D_MODEL, L.q_b, 1.f);
+      RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.q, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
       GemmArgs k;
       memset(&k, 0, sizeof(k));
       k.M = B;
       k.nk = D_MODEL / 64;
       k.R = S + Tl;
       k.G = 128 / k.R;
-      k.slots = e->d_slots;
+      k.slots = ln.slots;
       k.out = kvout;
       k.ldo = 2 * D_MODEL;
       k.bias = L.kv_b;
@@ -970,63 +1005,62 @@ static int run_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     }
     KLAUNCH(launch_kernel(attention_kernel, dim3(B * N_HEADS), dim3(64), 0, st, e->pdl, at));
     {
-      GemmArgs a = dense_args(M, D_MODEL, e->ctx, r, D_MODEL, L.wo_b, 1.f);
-      RC((gemm<G_RESID, BN_RESID>(e, st, e->m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+      GemmArgs a = dense_args(M, D_MODEL, ln.ctx, r, D_MODEL, L.wo_b, 1.f);
+      RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
     }
     // ---- convolution module
-    RC(run_norm(e, st, r, nullptr, L.n_conv, e->n, M));
+    RC(run_norm(e, ln, st, r, nullptr, L.n_conv, ln.n, M));
     {
-      GemmArgs a = dense_args(M, D_MODEL, e->n, e->g, D_MODEL, L.pw1_b, 1.f);
-      RC((gemm<G_GLU, BN_GLU>(e, st, e->m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+      GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
+      RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
     }
     {
       DwArgs d;
-      d.g = e->g;
+      d.g = ln.g;
       d.cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;
       d.cache_slot_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
-      d.slots = e->d_slots;
+      d.slots = ln.slots;
       d.w = L.dw_w;
       d.bias = L.dw_b;
-      d.e = e->ebuf;
+      d.e = ln.ebuf;
       d.T = Tl;
       KLAUNCH(launch_kernel(dwconv_kernel, dim3(B, 2), dim3(96), 0, st, e->pdl, d));
     }
     {
-      GemmArgs a = dense_args(M, D_MODEL, e->ebuf, r, D_MODEL, L.pw2_b, 1.f);
-      RC((gemm<G_RESID, BN_RESID>(e, st, e->m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+      GemmArgs a = dense_args(M, D_MODEL, ln.ebuf, r, D_MODEL, L.pw2_b, 1.f);
+      RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
     }
     // ---- second feed-forward, norm_out and what follows the layer
-    RC(run_norm(e, st, r, nullptr, L.n_ff2, e->n, M));
-    RC(run_ff(e, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff));
+    RC(run_norm(e, ln, st, r, nullptr, L.n_ff2, ln.n, M));
+    RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff));
     if (l == 6) {
-      RC(run_norm(e, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
-      RedArgs ra{e->r_full, e->st_red, e->d_slots, e->red_dw_w, e->red_dw_b, e->m_red, T, T2};
+      RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
+      RedArgs ra{ln.r_full, e->st_red, ln.slots, e->red_dw_w, e->red_dw_b, ln.m_red, T, T2};
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
-      GemmArgs a = dense_args(M2, D_FF, e->m_red, e->r_red, D_MODEL, e->red_pw_b, 1.f);
-      RC((gemm<G_STORE_F32, BN_STORE>(e, st, e->m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
-      RC(run_norm(e, st, e->r_red, nullptr, e->L[7].n_ff1, e->n, M2));
-      RC(tap(1 + l, e->r_red, M2));
+      GemmArgs a = dense_args(M2, D_FF, ln.m_red, ln.r_red, D_MODEL, e->red_pw_b, 1.f);
+      RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
+      RC(run_norm(e, ln, st, ln.r_red, nullptr, e->L[7].n_ff1, ln.n, M2));
+      RC(tap(1 + l, ln.r_red, M2));
     } else if (l == 14) {
-      UpsampleArgs ua{e->r_full, e->r_red, ff.part, ff.nsplit, ff.stride, ff.bias, ff.scale,
-                      L.n_out, e->L[15].n_ff1, e->n, B, T, T2};
+      UpsampleArgs ua{ln.r_full, ln.r_red, ff.part, ff.nsplit, ff.stride, ff.bias, ff.scale,
+                      L.n_out, e->L[15].n_ff1, ln.n, B, T, T2};
       KLAUNCH(launch_kernel(upsample_norm_kernel, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
-      RC(tap(1 + l, e->r_full, B * T));
+      RC(tap(1 + l, ln.r_full, B * T));
     } else if (l == 15) {
-      RC(run_norm(e, st, r, L.n_out, nullptr, e->n, M, ff));
+      RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     } else {
-      RC(run_norm(e, st, r, L.n_out, e->L[l + 1].n_ff1, e->n, M, ff));
+      RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     }
   }
   {
     M = B * T;
-    GemmArgs a = dense_args(M, D_MODEL, e->n, e->logprobs, N_CLASSES, e->dec_b, 1.f);
-    a.tokens = e->d_tokens;
-    RC((gemm<G_DECODER, DEC_PAD>(e, st, e->m_n, e->dec_w, a, (M + 127) / 128, 1, M, N_CLASSES)));
+    GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.lp_out, N_CLASSES, e->dec_b, 1.f);
+    a.tokens = ln.tok_out;
+    RC((gemm<G_DECODER, DEC_PAD>(e, st, ln.m_n, e->dec_w, a, (M + 127) / 128, 1, M, N_CLASSES)));
   }
-  e->launches_per_step = e->launches;
   return 0;
 }
 
@@ -1037,13 +1071,43 @@ static int check_step_args(tone_engine* e, int B) {
   return 0;
 }
 
+// Cut the batch into lanes and enqueue their kernel chains: lane 0 on `st`, the others on their own streams between
+// a fork event and per-lane join events (works both eagerly and under stream capture).
+static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
+  int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
+  if (const char* v = getenv("TONE_FORCE_LANES")) nl = std::max(1, std::min(e->n_lanes, atoi(v)));
+  nl = std::min(nl, B);
+  e->launches = 0;
+  const int per = (B + nl - 1) / nl;
+  if (nl > 1) CK(cudaEventRecord(e->fork_ev, st));
+  for (int li = 0; li < nl; ++li) {
+    tone_engine::Lane& ln = e->lanes[li];
+    const int b0 = li * per, nb = std::min(per, B - b0);
+    if (nb <= 0) continue;
+    ln.slots = e->d_slots + b0;
+    ln.pcm = e->d_pcm + (size_t)b0 * e->C;
+    ln.len_in = e->d_len_in + b0;
+    ln.lp_out = e->logprobs + (size_t)b0 * e->T * N_CLASSES;
+    ln.tok_out = e->d_tokens + (size_t)b0 * e->T;
+    cudaStream_t ls = li == 0 ? st : ln.stream;
+    if (li > 0) CK(cudaStreamWaitEvent(ls, e->fork_ev, 0));
+    RC(run_step(e, ln, nb, ls, taps));
+    if (li > 0) {
+      CK(cudaEventRecord(ln.done, ls));
+      CK(cudaStreamWaitEvent(st, ln.done, 0));
+    }
+  }
+  e->launches_per_step = e->launches;
+  return 0;
+}
+
 static int launch_step(tone_engine* e, int B, cudaStream_t st) {
-  if (!e->cfg.use_graph) return run_step(e, B, st, nullptr);
+  if (!e->cfg.use_graph) return enqueue_step(e, B, st, nullptr);
   auto it = e->graphs.find(B);
   if (it == e->graphs.end()) {
     cudaGraph_t graph;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = run_step(e, B, e->stream, nullptr);
+    int rc = enqueue_step(e, B, e->stream, nullptr);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(TONE_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
@@ -1121,7 +1185,7 @@ extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const 
 extern "C" int tone_step_debug(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
                                int32_t* tokens, float* taps) {
   RC(tone_stage(e, B, slots, pcm));
-  RC(run_step(e, B, e->stream, taps));
+  RC(enqueue_step(e, B, e->stream, taps));
   return tone_fetch(e, B, logprobs, tokens);
 }
 
