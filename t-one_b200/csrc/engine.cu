@@ -118,7 +118,8 @@ struct tone_engine {
   float *conv0_alpha, *conv0_beta, *conv1_alpha, *conv1_beta, *pre_norm_g, *out_norm_g;
   float *red_dw_w, *red_dw_b, *red_pw_b, *dec_b;
   LayerW L[16];
-  float *basis, *mel_w, *rope_cos, *rope_sin;
+  __half* basis;
+  float *mel_w, *rope_cos, *rope_sin;
   int* mel_start;
   unsigned char* mel_bin;
 
@@ -384,7 +385,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_KV, BN_KV>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
-  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
   return TONE_OK;
@@ -478,16 +479,27 @@ static int finalize_frontend(tone_engine* e) {
       basis[(size_t)k * WIN + j] = cos(ang) * hann;
       basis[(size_t)(N_BINS + k) * WIN + j] = -sin(ang) * hann;
     }
-  std::vector<float> bt((size_t)WIN * 162);
+  // fp16 hi/lo split, [2][BASIS_N][BASIS_LD], zero padded: the frontend kernel feeds it to mma.sync with the fp16
+  // waveform; hi + lo carries ~22 bits of the fp32 basis the reference uses
+  std::vector<uint16_t> bt((size_t)2 * BASIS_N * BASIS_LD, 0);
   for (int k = 0; k < 162; ++k)
     for (int j = 0; j < WIN; ++j) {
       double v = basis[(size_t)k * WIN + j];
       if (j + 1 < WIN) v -= 0.97 * basis[(size_t)k * WIN + j + 1];
       if (j == 0) v -= 0.97 * basis[(size_t)k * WIN];
-      bt[(size_t)j * 162 + k] = (float)v;
+      const float vf = (float)v;
+      const uint16_t hi = f2h(vf);
+      const uint16_t lo = f2h(vf - h2f(hi));
+      bt[(size_t)k * BASIS_LD + j] = hi;
+      bt[((size_t)BASIS_N + k) * BASIS_LD + j] = lo;
     }
-  int rc = upload_f32(e, bt, &e->basis);
-  if (rc) return rc;
+  int rc = 0;
+  {
+    void* pb = arena_take(e, bt.size() * 2);
+    if (!pb) return fail(TONE_ENOMEM, "weight arena exhausted");
+    CK(cudaMemcpy(pb, bt.data(), bt.size() * 2, cudaMemcpyHostToDevice));
+    e->basis = (__half*)pb;
+  }
   // slaney mel filterbank in CSR form (feats.py:82-93; torchaudio melscale_fbanks, slaney scale + norm)
   auto hz2mel = [](double f) {
     const double f_sp = 200.0 / 3, logstep = log(6.4) / 27.0;
@@ -880,7 +892,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     a.F = F;
     a.T = T;
     a.T2 = T2;
-    const size_t smem = (size_t)(C + HOP + F * 162 + F * N_MELS + WIN * 162) * 4;
+    const int n_mt = (F + 15) / 16, UH = ((16 * n_mt * HOP + HOP + 16) + 7) & ~7;
+    const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4;
     KLAUNCH(launch_kernel(begin_step_kernel, dim3(B), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
   }
   {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels

@@ -40,8 +40,8 @@ struct BeginArgs {
   bf16* kv15;                // [slots][KV_ROWS_MAX][384]   layer-15 [cache | new] rows (30 + T)
   int* mhsa_len;             // [slots]
   int* len_in;               // [B] length seen by this step's masks (value entering the step)
-  const float* basis;        // [160][162] pre-emphasis * Hann * DFT, column k = cos bin k / -sin bin k-81
-  const float* hann_unused;
+  const __half* basis;       // [2][168][168] fp16 hi / lo split of the fused pre-emphasis * Hann * DFT basis, row n =
+                             // cos bin n (n < 81) / -sin bin n-81, k contiguous, zero padded
   const int* mel_start;      // [65] CSR over mel filters
   const unsigned char* mel_bin;  // [nnz]
   const float* mel_w;        // [nnz]
@@ -49,33 +49,46 @@ struct BeginArgs {
   int C, F, T, T2;
 };
 
-// One CTA per stream.  352 threads: threads [0,162) accumulate DFT column k for the first half of the frames,
-// threads [162,324) the same columns for the second half.
+// One CTA per stream, 352 threads (11 warps).  The framed DFT runs on the tensor cores as an fp16 GEMM with fp32
+// accumulation: the waveform IS fp16 (the reference quantises it, model.py:165), so the A operand is exact, and the
+// fused (pre-emphasis x Hann x DFT) basis is split into an fp16 high and low part (b = hi + lo, ~22 bits), i.e. two
+// MMAs per tile: spec[f][n] = sum_k u[80 f + k] * (hi[n][k] + lo[n][k]).
 constexpr int BEGIN_THREADS = 352;
+constexpr int BASIS_N = 168;             // 162 columns (81 cos + 81 sin) padded to 21 n-tiles of 8
+constexpr int BASIS_LD = 168;            // halfs per basis row: 160 k + 8 pad (conflict-free fragment loads)
+
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
 __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginArgs a) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(16) unsigned char sm_raw[];
   PROF_DECL();
   PROF_BEGIN(1);
   pdl_launch_dependents();
   const int F = a.F, C = a.C;
-  float* u = sm;                          // [C + 80]
-  float* spec = u + (C + 80);             // [F][162]
-  float* featS = spec + F * 162;          // [F][64]
-  float* basisS = featS + F * N_MELS;     // [160][162] constant basis, staged before the PDL wait
+  const int n_mt = (F + 15) / 16;                       // frame tiles of 16
+  const int UH = 16 * n_mt * HOP + HOP + 16;            // halfs: frames of the padded tiles stay in bounds
+  __half* basisS = reinterpret_cast<__half*>(sm_raw);   // [2][BASIS_N][BASIS_LD] hi, lo
+  __half* uh = basisS + 2 * BASIS_N * BASIS_LD;         // [UH] carried 80 samples + chunk, zero tail
+  float* spec = reinterpret_cast<float*>(uh + ((UH + 7) & ~7));   // [F][162]
+  float* featS = spec + F * 162;                        // [F][64]
   const int b = blockIdx.x, tid = threadIdx.x;
-  {
-    const float4* src = reinterpret_cast<const float4*>(a.basis);
-    float4* dst = reinterpret_cast<float4*>(basisS);
-    constexpr int N4 = WIN * 162 / 4;     // 6480
-    for (int i0 = 0; i0 < N4; i0 += 4 * BEGIN_THREADS) {
-      float4 t[4];
+  {  // constant basis -> smem, before the PDL wait (it does not depend on the previous kernel)
+    const uint4* src = reinterpret_cast<const uint4*>(a.basis);
+    uint4* dst = reinterpret_cast<uint4*>(basisS);
+    constexpr int N16 = 2 * BASIS_N * BASIS_LD * 2 / 16;   // 7056
+    for (int i0 = 0; i0 < N16; i0 += 4 * BEGIN_THREADS) {
+      uint4 t[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (i0 + q * BEGIN_THREADS + tid < N4) t[q] = __ldg(src + i0 + q * BEGIN_THREADS + tid);
+        if (i0 + q * BEGIN_THREADS + tid < N16) t[q] = __ldg(src + i0 + q * BEGIN_THREADS + tid);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (i0 + q * BEGIN_THREADS + tid < N4) dst[i0 + q * BEGIN_THREADS + tid] = t[q];
+        if (i0 + q * BEGIN_THREADS + tid < N16) dst[i0 + q * BEGIN_THREADS + tid] = t[q];
     }
   }
   pdl_wait();
@@ -88,7 +101,15 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     uint4* f4 = reinterpret_cast<uint4*>(a.feat + (size_t)slot * FEAT_ROWS_MAX * N_MELS);
     if (tid < SUB1_ROWS * N_MELS / 8) f4[tid] = f4[F * N_MELS / 8 + tid];
     uint4* x4 = reinterpret_cast<uint4*>(a.x1 + (size_t)slot * X1_ROWS_MAX * X1_ROW);
-    for (int i = tid; i < SUB2_ROWS * X1_ROW / 8; i += BEGIN_THREADS) x4[i] = x4[F * X1_ROW / 8 + i];
+    {
+      uint4 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (tid + q * BEGIN_THREADS < SUB2_ROWS * X1_ROW / 8) t[q] = x4[F * X1_ROW / 8 + tid + q * BEGIN_THREADS];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (tid + q * BEGIN_THREADS < SUB2_ROWS * X1_ROW / 8) x4[tid + q * BEGIN_THREADS] = t[q];
+    }
     // attention caches overlap their source: load everything, barrier, store
     uint4* k15 = reinterpret_cast<uint4*>(a.kv15 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
     uint4* k14 = reinterpret_cast<uint4*>(a.kv14 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
@@ -103,6 +124,15 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     for (int i = 0; i < 3; ++i) {
       int idx = tid + i * BEGIN_THREADS;
       if (idx < (MHSA_S / 2) * RV) r14[i] = k14[a.T2 * RV + idx];
+    }
+    // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
+    __half* pre = a.pre + (size_t)slot * HOP;
+    const int* pcm = a.pcm + (size_t)b * C;
+    for (int i = tid; i < UH; i += BEGIN_THREADS) {
+      __half v = __float2half_rn(0.f);
+      if (i < HOP) v = pre[i];
+      else if (i < C + HOP) v = __float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f);
+      uh[i] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -120,49 +150,46 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
       a.len_in[b] = len;
       a.mhsa_len[slot] = min(len + a.T, MHSA_S);   // conformer_blocks.py:191
     }
+    for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = uh[C + i];
   }
-
-  // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
-  __half* pre = a.pre + (size_t)slot * HOP;
-  const int* pcm = a.pcm + (size_t)b * C;
-  for (int i = tid; i < C + HOP; i += BEGIN_THREADS) {
-    float v;
-    if (i < HOP) v = __half2float(pre[i]);
-    else v = __half2float(__float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f));
-    u[i] = v;
-  }
-  __syncthreads();
   if (threadIdx.x == 0) PROF_MARK(1);
-  for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = __float2half_rn(u[C + i]);
 
-  // ---- framed DFT through the fused (pre-emphasis x Hann x DFT) basis: spec[f][k] = sum_j u[80 f + j] * basis[j][k]
+  // ---- framed DFT on the tensor cores: warp w owns n-tiles w, w+11 (21 tiles of 8 columns)
   {
-    const int half = (F + 1) / 2;
-    const int grp = tid / 162;            // 0, 1 (threads >= 324 idle here)
-    const int k = tid - grp * 162;
-    if (grp < 2) {
-      const int f0 = grp * half;
-      const int nf = min(half, F - f0);
-      float acc[MAX_FRAMES / 2];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    for (int nt = warp; nt < BASIS_N / 8; nt += BEGIN_THREADS / 32) {
+      const __half* bh = basisS + (nt * 8 + g) * BASIS_LD + 2 * t;
+      const __half* bl = bh + BASIS_N * BASIS_LD;
+      for (int mt = 0; mt < n_mt; ++mt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const __half* ua = uh + (mt * 16 + g) * HOP + 2 * t;
 #pragma unroll
-      for (int f = 0; f < MAX_FRAMES / 2; ++f) acc[f] = 0.f;
-      for (int j = 0; j < WIN; j += 4) {
-        const float b0 = basisS[(j + 0) * 162 + k], b1 = basisS[(j + 1) * 162 + k];
-        const float b2 = basisS[(j + 2) * 162 + k], b3 = basisS[(j + 3) * 162 + k];
-#pragma unroll
-        for (int f = 0; f < MAX_FRAMES / 2; ++f) {
-          if (f < nf) {
-            const float4 y = *reinterpret_cast<const float4*>(&u[(f0 + f) * HOP + j]);
-            acc[f] = fmaf(b0, y.x, acc[f]);
-            acc[f] = fmaf(b1, y.y, acc[f]);
-            acc[f] = fmaf(b2, y.z, acc[f]);
-            acc[f] = fmaf(b3, y.w, acc[f]);
+        for (int ks = 0; ks < WIN / 16; ++ks) {
+          uint32_t af[4], bhf[2], blf[2];
+          af[0] = *reinterpret_cast<const uint32_t*>(ua + ks * 16);
+          af[1] = *reinterpret_cast<const uint32_t*>(ua + 8 * HOP + ks * 16);
+          af[2] = *reinterpret_cast<const uint32_t*>(ua + ks * 16 + 8);
+          af[3] = *reinterpret_cast<const uint32_t*>(ua + 8 * HOP + ks * 16 + 8);
+          bhf[0] = *reinterpret_cast<const uint32_t*>(bh + ks * 16);
+          bhf[1] = *reinterpret_cast<const uint32_t*>(bh + ks * 16 + 8);
+          blf[0] = *reinterpret_cast<const uint32_t*>(bl + ks * 16);
+          blf[1] = *reinterpret_cast<const uint32_t*>(bl + ks * 16 + 8);
+          mma_f16_16x8x16(acc, af, bhf);
+          mma_f16_16x8x16(acc, af, blf);
+        }
+        const int n = nt * 8 + 2 * t, f0 = mt * 16 + g;
+        if (n < 162) {
+          if (f0 < F) {
+            spec[f0 * 162 + n] = acc[0];
+            spec[f0 * 162 + n + 1] = acc[1];
+          }
+          if (f0 + 8 < F) {
+            spec[(f0 + 8) * 162 + n] = acc[2];
+            spec[(f0 + 8) * 162 + n + 1] = acc[3];
           }
         }
       }
-#pragma unroll
-      for (int f = 0; f < MAX_FRAMES / 2; ++f)
-        if (f < nf) spec[(f0 + f) * 162 + k] = acc[f];
     }
   }
   __syncthreads();
