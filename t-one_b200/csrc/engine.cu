@@ -164,6 +164,9 @@ struct tone_engine {
   std::unordered_map<int, cudaGraphExec_t> graphs;
   int launches = 0, launches_per_step = 0;
   bool pdl = true;      // programmatic dependent launch between the kernels of a step (TONE_PDL=0 disables)
+  // conv module's GLU GEMM + depthwise conv in one kernel (TONE_FUSE_DW=1).  Correct but measured SLOWER on B200
+  // (19.9 us vs 3.8 + 7.0 us): four epilogue warps per CTA cannot keep enough cache-column loads in flight.
+  bool fuse_dw = false;
   int num_sms = 148;
 };
 
@@ -273,6 +276,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("TONE_PDL")) e->pdl = atoi(v) != 0;
+  if (const char* v = getenv("TONE_FUSE_DW")) e->fuse_dw = atoi(v) != 0;
   e->C = cfg->chunk_samples;
   e->F = e->C / HOP;
   e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
@@ -385,6 +389,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_KV, BN_KV>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
+  CK((configure_gemm_tc<G_GLU_DW, BN_GLU>()));
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
@@ -1023,11 +1028,22 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     }
     // ---- convolution module
     RC(run_norm(e, ln, st, r, nullptr, L.n_conv, ln.n, M));
-    {
-      GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
-      RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
-    }
-    {
+    if (e->cfg.gemm_impl == 0 && e->fuse_dw) {
+      // pointwise conv 1 + GLU + causal depthwise conv + BN + SiLU + cache roll in ONE kernel: tiles hold whole streams
+      GemmArgs a = dense_args(B, D_MODEL, ln.n, ln.ebuf, D_MODEL, L.pw1_b, 1.f);
+      a.R = Tl;
+      a.G = std::min(128 / Tl, 12);      // whole streams per tile; each epilogue warp keeps 3 cache columns in registers
+      a.slots = ln.slots;
+      a.dw_cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;
+      a.dw_cache_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
+      a.dw_w = L.dw_w;
+      a.dw_b = L.dw_b;
+      RC((gemm<G_GLU_DW, BN_GLU>(e, st, ln.m_n, L.pw1, a, (B + a.G - 1) / a.G, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+    } else {
+      {
+        GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
+        RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+      }
       DwArgs d;
       d.g = ln.g;
       d.cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;

@@ -26,6 +26,8 @@ enum GemmKind : int {
   G_KV = 6,         // out fp32 = acc + bias, gather A from [cache|new] rows (layers 14, 15)
   G_DECODER = 7,    // logprobs = log_softmax(acc + bias)[0:35], argmax      (BN = 48)
   G_PARTIAL = 8,    // part[z] fp32 = acc over K slice z (split-K; blockIdx.z)  (ff down; summed by addnorm_kernel)
+  G_GLU_DW = 9,     // conv module in one kernel: GLU epilogue, then the causal depthwise conv k=31 + BN + SiLU over
+                    // [30-row cache | T new rows] per stream and channel, cache roll included (tiles hold whole streams)
 };
 
 struct GemmArgs {
@@ -43,6 +45,11 @@ struct GemmArgs {
   int out_row_off;            // G_CONV0: first row written inside a slot (the cached rows come first)
   int* tokens;                // G_DECODER
   long long z_stride;         // G_PARTIAL: elements between the partial outputs of consecutive K slices
+  // G_GLU_DW: depthwise stage
+  bf16* dw_cache;             // [slots][16][30][384], layer offset applied
+  long long dw_cache_stride;  // elements between slots
+  const float* dw_w;          // [31][384] BN-folded taps
+  const float* dw_b;          // [384]
   // Raw operand views, used only by the SIMT debug kernels (gemm_ref.cuh); the tensor-core path reads through
   // the tensor maps.
   const bf16* A;
@@ -55,6 +62,8 @@ struct GemmArgs {
 template <int KIND>
 struct KindTraits {
   static constexpr bool gather = (KIND == G_CONV0 || KIND == G_CONV1 || KIND == G_KV);
+  // rows of a tile are G whole streams x R frames (gather kinds, and dense kinds that need whole streams per tile)
+  static constexpr bool stream_rows = gather || (KIND == G_GLU_DW);
 };
 
 // DEEP = one CTA per SM with the whole shared memory as the operand ring: the small-batch GEMMs of this model are
@@ -65,7 +74,8 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGES = DEEP ? (200 * 1024) / (A_BYTES + B_BYTES) : ((BN > 64) ? 3 : 4);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024 + 1024;  // + barriers + constants + alignment slack
+  // + barriers (256) + per-column constants (1 KB) + depthwise taps of G_GLU_DW (33 x 32 floats) + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024 + 4352 + 1024;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogues
@@ -78,7 +88,7 @@ struct RowInfo {
 template <int KIND>
 __device__ __forceinline__ RowInfo row_info(const GemmArgs& a, int row_in_tile) {
   RowInfo ri;
-  if constexpr (KindTraits<KIND>::gather) {
+  if constexpr (KindTraits<KIND>::stream_rows) {
     int g = row_in_tile / a.R;
     int j = row_in_tile - g * a.R;
     int b = blockIdx.x * a.G + g;
@@ -112,6 +122,14 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
     }
   } else if constexpr (KIND == G_DECODER) {
     if (t < 48) s_c0[t] = t < 35 ? __ldg(a.bias + t) : 0.f;
+  } else if constexpr (KIND == G_GLU_DW) {
+    if (t < BN) s_c0[t] = __ldg(a.bias + n0 + t);
+    // depthwise taps [31][32] + bias [32] of this tile's 32 channels, behind the per-column constants
+    float* wS = s_c1 + 128;
+    for (int i = t; i < 32 * 32; i += 128) {
+      const int j = i >> 5, c = i & 31;
+      wS[i] = (j < 31) ? __ldg(a.dw_w + j * 384 + blockIdx.y * 32 + c) : __ldg(a.dw_b + blockIdx.y * 32 + c);
+    }
   } else {
     if (t < BN) s_c0[t] = a.bias ? __ldg(a.bias + n0 + t) : 0.f;
   }
@@ -121,7 +139,7 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
 template <int KIND, int BN>
 struct OutCfg {
   static constexpr bool f32 = (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_PARTIAL || KIND == G_RESID);
-  static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU) ? BN : BN * 2);
+  static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) ? BN : BN * 2);
   static constexpr int STRIDE = ROW_BYTES + 16;   // +16 B: float4 stores of a quarter-warp hit distinct banks
   static constexpr int LPR = ROW_BYTES / 16;      // lanes per output row in the coalesced phase
   static constexpr int RPI = 32 / LPR;            // rows per warp instruction
@@ -183,7 +201,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
     return;
   } else {
     // element offset of this tile's first output column
-    const int n0_out = (KIND == G_SWIGLU || KIND == G_GLU) ? blockIdx.y * (BN / 2) : n0;
+    const int n0_out = (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) ? blockIdx.y * (BN / 2) : n0;
     // phase-2 geometry (also used to prefetch the residual before the accumulator is ready)
     const int sub_row = lane / O::LPR, cb = (lane % O::LPR) * 16;
     float4 rres[32 / O::RPI];
@@ -192,6 +210,19 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       for (int it = 0; it < 32 / O::RPI; ++it) {
         const RowInfo ri = row_info<KIND>(a, q * 32 + it * O::RPI + sub_row);
         if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
+      }
+    }
+    // G_GLU_DW: the cached depthwise columns of this warp's (up to 3) streams are fetched while the main loop runs
+    float dwc[KIND == G_GLU_DW ? 3 : 1][KIND == G_GLU_DW ? 30 : 1];
+    if constexpr (KIND == G_GLU_DW) {
+#pragma unroll
+      for (int si = 0; si < 3; ++si) {
+        const int g = q + 4 * si, b = blockIdx.x * a.G + g;
+        if (g < a.G && b < a.M) {
+          const bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + blockIdx.y * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 30; ++i) dwc[si][i] = __bfloat162float(cache[i * 384]);
+        }
       }
     }
     mbar_wait(tmem_full, 0);
@@ -222,7 +253,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         }
         sts128(srow + c * 4, o);
       }
-    } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
+    } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) {
       constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
 #pragma unroll
       for (int c = 0; c < HW; c += 8) {
@@ -252,6 +283,54 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
                                          pack_bf16x2(r[6], r[7])));
       }
+    }
+    if constexpr (KIND == G_GLU_DW) {
+      // ---- depthwise stage: warp w takes streams w, w+4, ... of this tile, lane = channel.  Column = [30 cached
+      // rows | T new rows from the staged GLU tile]; e = silu(b' + sum_j w'[j] col[t+j]); cache' = last 30 rows.
+      static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the whole GLU tile is staged
+      const int T = a.R;
+      const int cg = blockIdx.y * 32 + lane;            // global channel
+      const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
+      const float bias = wS[31 * 32 + lane];
+#pragma unroll
+      for (int si = 0; si < 3; ++si) {
+        const int g = q + 4 * si, b = blockIdx.x * a.G + g;
+        if (g < a.G && b < a.M) {
+          bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
+          float col[30 + 13];
+#pragma unroll
+          for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
+#pragma unroll
+          for (int t = 0; t < 13; ++t)
+            if (t < T)
+              col[30 + t] =
+                  __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
+          float acc2[13];
+#pragma unroll
+          for (int t = 0; t < 13; ++t) acc2[t] = bias;
+#pragma unroll
+          for (int j = 0; j < 31; ++j) {
+            const float wj = wS[j * 32 + lane];
+#pragma unroll
+            for (int t = 0; t < 13; ++t)
+              if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
+          }
+          bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
+#pragma unroll
+          for (int t = 0; t < 13; ++t)
+            if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
+#pragma unroll
+          for (int i = 0; i < 30; ++i) {
+            float vsel = col[i];
+#pragma unroll
+            for (int t = 1; t <= 13; ++t)
+              if (t == T) vsel = col[i + t];
+            cache[i * 384] = __float2bfloat16(vsel);
+          }
+        }
+      }
+      return;
     }
     __syncwarp();
 
@@ -379,7 +458,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             for (int g = 0; g < nvalid; ++g)
               tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
         } else {
-          tma_load_2d(dA, &tmA, &full[s], kz + it * 64, blockIdx.x * 128);
+          tma_load_2d(dA, &tmA, &full[s], kz + it * 64,
+                      (KIND == G_GLU_DW) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
         }
       }
     }
