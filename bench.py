@@ -90,6 +90,12 @@ def cpu_port_throughput(streams: int, chunk: int, budget_s: float, warmup: int =
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tone_oracle as orc
     tb = importlib.import_module("t-one_b200")
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would pin us to one)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     W = orc.to_torch(tb.weights.init_weights(0))
     n_chunks = 4
     pcm = tb.synth.telephony_pcm(streams, chunk * n_chunks, seed=1234)

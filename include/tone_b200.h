@@ -94,6 +94,13 @@ int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream);
 int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens);
 int tone_sync(tone_engine* e);
 
+/* Greedy fast path: instead of the full log-probs, fetch per frame the argmax token and the two
+ * log-probs the phrase splitter thresholds on - ' ' (id 33) and blank (id 34), tone/logprob_splitter.py:129.
+ *   tokens        host int32 [B][frames_out]
+ *   sil_logprobs  host fp32  [B][frames_out][2]
+ * Greedy decoding of a phrase needs nothing else (tone/decoder.py:57-59), so D2H drops from 140 to 12 bytes/frame. */
+int tone_fetch_greedy(tone_engine* e, int32_t B, int32_t* tokens, float* sil_logprobs);
+
 /* Device-pointer form of the step for GPU-resident producers/consumers (the role of Triton's
  * GPU tensors between ensemble stages, triton/ensemble/config.pbtxt:20-55): slots / pcm are
  * device int32 buffers, logprobs / tokens device outputs (any may be NULL = use what is staged /

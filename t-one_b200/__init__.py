@@ -5,9 +5,9 @@ Host-side mirror of the reference's acoustic-model interface
 The directory name carries a hyphen; import it as ``importlib.import_module("t-one_b200")``
 or through the ``tone_b200`` alias module at the repo root.
 """
-from . import arch, model, sharding, synth, weights  # noqa: F401
+from . import arch, greedy, model, scheduler, sharding, state_formats, synth, weights  # noqa: F401
 from .arch import DEFAULT_ARCH, LABELS, ToneArch  # noqa: F401
 from .model import B200StreamingCTCModel, Engine, StreamSlots, load_library  # noqa: F401
 
-__all__ = ["arch", "model", "sharding", "synth", "weights", "DEFAULT_ARCH", "LABELS", "ToneArch",
+__all__ = ["arch", "greedy", "model", "scheduler", "sharding", "state_formats", "synth", "weights", "DEFAULT_ARCH", "LABELS", "ToneArch",
            "B200StreamingCTCModel", "Engine", "StreamSlots", "load_library"]

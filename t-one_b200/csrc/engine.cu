@@ -135,6 +135,7 @@ struct tone_engine {
   int rows_alloc;
   int *d_slots, *d_pcm, *d_len_in, *d_tokens;
   float* logprobs;
+  float* d_aux;      // [rows][2] logprob of space / blank per frame (greedy fast path)
   int max_splits = 8;
   CUtensorMap m_feat, m_x1, m_kv14, m_kv15;
   CUtensorMap w_feat, w_x1, w_kv14, w_kv15;   // same views with a box spanning the G slots of one tile
@@ -152,6 +153,7 @@ struct tone_engine {
     int* len_in;
     float* lp_out;
     int* tok_out;
+    float* aux_out;
   };
   std::vector<Lane> lanes;
   int n_lanes = 2, lane_min_batch = 256;   // measured: lanes only pay once kernels are throughput bound (B >= 512)
@@ -159,7 +161,7 @@ struct tone_engine {
 
   // pinned staging
   int *p_slots, *p_pcm, *p_tokens;
-  float* p_logprobs;
+  float *p_logprobs, *p_aux;
 
   std::unordered_map<int, cudaGraphExec_t> graphs;
   int launches = 0, launches_per_step = 0;
@@ -315,6 +317,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   rc |= dev_alloc(e, &e->d_pcm, Bm * e->C);
   rc |= dev_alloc(e, &e->d_len_in, Bm);
   rc |= dev_alloc(e, &e->d_tokens, R);
+  rc |= dev_alloc(e, &e->d_aux, R * 2);
   rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
   if (const char* v = getenv("TONE_LANES")) e->n_lanes = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("TONE_LANE_MIN_BATCH")) e->lane_min_batch = std::max(1, atoi(v));
@@ -345,6 +348,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK(cudaMallocHost((void**)&e->p_pcm, Bm * e->C * 4));
   CK(cudaMallocHost((void**)&e->p_tokens, Bm * MAX_T * 4));
   CK(cudaMallocHost((void**)&e->p_logprobs, Bm * MAX_T * N_CLASSES * 4));
+  CK(cudaMallocHost((void**)&e->p_aux, Bm * MAX_T * 2 * 4));
 
   // activation-side tensor maps
   {
@@ -412,6 +416,7 @@ extern "C" void tone_destroy(tone_engine* e) {
   cudaFreeHost(e->p_pcm);
   cudaFreeHost(e->p_tokens);
   cudaFreeHost(e->p_logprobs);
+  cudaFreeHost(e->p_aux);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1088,6 +1093,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     M = B * T;
     GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.lp_out, N_CLASSES, e->dec_b, 1.f);
     a.tokens = ln.tok_out;
+    a.aux = ln.aux_out;
     RC((gemm<G_DECODER, DEC_PAD>(e, st, ln.m_n, e->dec_w, a, (M + 127) / 128, 1, M, N_CLASSES)));
   }
   return 0;
@@ -1118,6 +1124,7 @@ static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     ln.len_in = e->d_len_in + b0;
     ln.lp_out = e->logprobs + (size_t)b0 * e->T * N_CLASSES;
     ln.tok_out = e->d_tokens + (size_t)b0 * e->T;
+    ln.aux_out = e->d_aux + (size_t)b0 * e->T * 2;
     cudaStream_t ls = li == 0 ? st : ln.stream;
     if (li > 0) CK(cudaStreamWaitEvent(ls, e->fork_ev, 0));
     RC(run_step(e, ln, nb, ls, taps));
@@ -1194,6 +1201,21 @@ extern "C" int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* t
   CK(cudaStreamSynchronize(e->stream));
   if (logprobs && logprobs != e->p_logprobs) memcpy(logprobs, e->p_logprobs, nl);
   if (tokens && tokens != e->p_tokens) memcpy(tokens, e->p_tokens, nt);
+  return TONE_OK;
+}
+
+// Greedy fast path: per frame only the argmax token and the two log-probs the phrase splitter looks at
+// (tone/logprob_splitter.py:129: speech iff exp(lp[33]) + exp(lp[34]) <= 0.9) cross PCIe - 12 B instead of 140 B.
+extern "C" int tone_fetch_greedy(tone_engine* e, int32_t B, int32_t* tokens, float* sil_logprobs) {
+  RC(check_step_args(e, B));
+  if (!tokens || !sil_logprobs) return fail(TONE_EINVAL, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t nt = (size_t)B * e->T * 4, na = (size_t)B * e->T * 8;
+  CK(cudaMemcpyAsync(e->p_tokens, e->d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->p_aux, e->d_aux, na, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  memcpy(tokens, e->p_tokens, nt);
+  memcpy(sil_logprobs, e->p_aux, na);
   return TONE_OK;
 }
 

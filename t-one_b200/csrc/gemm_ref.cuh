@@ -113,6 +113,10 @@ __global__ void decoder_ref_kernel(const GemmArgs a) {
   float* out = reinterpret_cast<float*>(a.out) + (long long)row * 35;
   for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
   if (a.tokens) a.tokens[row] = am;
+  if (a.aux) {
+    a.aux[row * 2] = lg[33] - lse;
+    a.aux[row * 2 + 1] = lg[34] - lse;
+  }
 }
 
 template <int KIND, int BN>

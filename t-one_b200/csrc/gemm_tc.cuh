@@ -43,7 +43,8 @@ struct GemmArgs {
   float scale;
   long long out_slot_stride;  // G_CONV0: elements between consecutive slots of x1
   int out_row_off;            // G_CONV0: first row written inside a slot (the cached rows come first)
-  int* tokens;                // G_DECODER
+  int* tokens;                // G_DECODER: argmax per frame
+  float* aux;                 // G_DECODER: [rows][2] = logprob of ' ' (33) and of blank (34), what the phrase splitter needs
   long long z_stride;         // G_PARTIAL: elements between the partial outputs of consecutive K slices
   // G_GLU_DW: depthwise stage
   bf16* dw_cache;             // [slots][16][30][384], layer offset applied
@@ -197,6 +198,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 #pragma unroll
       for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
       if (a.tokens) a.tokens[ri.out_row] = am;
+      if (a.aux) *reinterpret_cast<float2*>(a.aux + ri.out_row * 2) = make_float2(lg[33] - lse, lg[34] - lse);
     }
     return;
   } else {

@@ -27,7 +27,7 @@ TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1,
 SYMBOLS = (
     "tone_create", "tone_destroy", "tone_get_info", "tone_last_error", "tone_load_weight",
     "tone_finalize_weights", "tone_alloc_slots", "tone_release_slots", "tone_reset_slots", "tone_step",
-    "tone_stage", "tone_step_staged", "tone_fetch", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
+    "tone_stage", "tone_step_staged", "tone_fetch", "tone_fetch_greedy", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
     "tone_import_state", "tone_step_debug", "tone_selftest_gemm",
 )
 
@@ -75,6 +75,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.tone_step_staged.argtypes = [vp, C.c_int32, vp]
     lib.tone_fetch.argtypes = [vp, C.c_int32, f32p, i32p]
     lib.tone_sync.argtypes = [vp]
+    lib.tone_fetch_greedy.argtypes = [vp, C.c_int32, i32p, f32p]
     lib.tone_step_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.tone_host_buffers.argtypes = [vp, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f32p), C.POINTER(i32p)]
     lib.tone_export_state.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
@@ -220,6 +221,21 @@ class Engine:
         lp = self.h_logprobs[: B * self.T * 35].reshape(B, self.T, 35)
         tk = self.h_tokens[: B * self.T].reshape(B, self.T)
         return lp, tk
+
+    def step_greedy(self, slots, pcm):
+        """Step and fetch only what greedy decoding needs: tokens int32 (B,T) and the (space, blank) log-probs
+        fp32 (B,T,2) that the phrase splitter thresholds on."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        x = np.ascontiguousarray(pcm, dtype=np.int32)
+        B = len(s)
+        if x.shape != (B, self.chunk_samples):
+            raise ValueError(f"pcm must be ({B}, {self.chunk_samples}), got {x.shape}")
+        self._ck(self._lib.tone_stage(self._h, B, _i32p(s), _i32p(x)))
+        self._ck(self._lib.tone_step_staged(self._h, B, None))
+        tk = np.empty((B, self.T), dtype=np.int32)
+        sil = np.empty((B, self.T, 2), dtype=np.float32)
+        self._ck(self._lib.tone_fetch_greedy(self._h, B, _i32p(tk), _f32p(sil)))
+        return tk, sil
 
     def step_pinned(self, B: int):
         """H2D of the pinned inputs + step + D2H into the pinned outputs, synchronous (the e2e path)."""
