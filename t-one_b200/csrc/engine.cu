@@ -86,11 +86,12 @@ struct WeightMat {      // a bf16 [N][K] matrix on the device with its TMA map (
   bf16* ptr = nullptr;
   int N = 0, K = 0;
   CUtensorMap map;
+  CUtensorMap map128;   // same matrix, box 64 x 128: the large-batch tile shape (valid when N % 128 == 0)
 };
 
 struct LayerW {
-  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw2;
-  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw2_b;
+  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw1w, pw2;   // pw1w: pw1 packed for 128-wide tiles
+  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw1w_b, *pw2_b;
   float *n_ff1, *n_att, *n_conv, *n_ff2, *n_out;
   float *qln_w, *qln_b, *kln_w, *kln_b;
   float *dw_w, *dw_b;
@@ -227,6 +228,10 @@ static int upload_mat(tone_engine* e, const std::vector<float>& w, int N, int K,
   out->ptr = (bf16*)p;
   out->N = N;
   out->K = K;
+  if (N % 128 == 0) {
+    int rc = make_map_2d(e, &out->map128, p, N, K, 128, true);
+    if (rc) return rc;
+  }
   return make_map_2d(e, &out->map, p, N, K, box_rows, true);
 }
 static const HostTensor* W(tone_engine* e, const std::string& name) {
@@ -256,6 +261,9 @@ static std::vector<float> concat(std::initializer_list<const std::vector<float>*
 
 // ------------------------------------------------------------------------------------------------ create / destroy
 static const int BN_SWIGLU = 128, BN_RESID = 32, BN_GLU = 64, BN_STORE = 64, BN_CONV = 128, BN_KV = 64, BN_PART = 128;
+// Narrow N tiles fill the SMs when there are only a few M tiles; from BIG_M rows on the 128-wide tile is used for
+// every GEMM so that the A tile is not re-read by 12 N-tile CTAs.
+static const int BIG_M = 2048;
 
 extern "C" const char* tone_last_error(void) { return g_err; }
 
@@ -394,6 +402,8 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
   CK((configure_gemm_tc<G_GLU_DW, BN_GLU>()));
+  CK((configure_gemm_tc<G_RESID, 128>()));
+  CK((configure_gemm_tc<G_GLU, 128>()));
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
@@ -695,6 +705,8 @@ static int finalize_layer(tone_engine* e, int l) {
     if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, BN_GLU / 2), 2 * D_MODEL, D_MODEL, BN_GLU, &L.pw1)))
       return rc;
     if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, BN_GLU / 2), &L.pw1_b))) return rc;
+    if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, 64), 2 * D_MODEL, D_MODEL, 128, &L.pw1w))) return rc;
+    if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, 64), &L.pw1w_b))) return rc;
   }
   NEEDW(dw, Cp + "depthwise_conv.conv.weight");
   NEEDW(dwb, Cp + "depthwise_conv.conv.bias");
@@ -795,12 +807,14 @@ extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slot
 // ------------------------------------------------------------------------------------------------ the step
 template <int KIND, int BN>
 static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const WeightMat& w, GemmArgs a, int m_tiles,
-                int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr, int splits = 1) {
+                int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr, int splits = 1,
+                bool box128 = false) {
   a.W = w.ptr;
   a.ldw = w.K;
   cudaError_t err;
   if (e->cfg.gemm_impl == 0)
-    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, w.map, a, m_tiles, n_tiles, e->pdl, e->num_sms, splits);
+    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, box128 ? w.map128 : w.map, a, m_tiles, n_tiles, e->pdl,
+                                   e->num_sms, splits);
   else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols, splits);
   e->launches++;
   if (err != cudaSuccess) return fail(TONE_ECUDA, "gemm kind %d launch: %s", KIND, cudaGetErrorString(err));
@@ -945,7 +959,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
   int M = B * T;
   {
     GemmArgs a = dense_args(M, SUB_OUT, ln.c1, ln.r_full, D_MODEL, nullptr, 1.f);
-    RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / BN_STORE, M, D_MODEL)));
+    if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+    else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_c1, e->out_w, a, (M + 127) / 128, D_MODEL / BN_STORE, M, D_MODEL)));
   }
   RC(run_norm(e, ln, st, ln.r_full, e->out_norm_g, e->L[0].n_ff1, ln.n, M));
   RC(tap(0, ln.r_full, M));
@@ -975,7 +990,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
         GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, 3 * D_MODEL, L.qkv_b, 1.f);
-        RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
+        if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / 128, M, 3 * D_MODEL, nullptr, 1, true)));
+        else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
         at.q = ln.qkv;
         at.k = ln.qkv + D_MODEL;
         at.v = ln.qkv + 2 * D_MODEL;
@@ -986,7 +1002,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
         at.k_ln_b = L.kln_b;
       } else {
         GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, D_MODEL, L.qkv_b, 1.f);
-        RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+        if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.qkv, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+        else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
         at.v = ln.qkv;
         at.ldv = D_MODEL;
       }
@@ -997,7 +1014,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       float* qbuf = ln.qkv;
       float* kvout = ln.qkv + (size_t)e->rows_alloc * D_MODEL;
       GemmArgs a = dense_args(M, D_MODEL, ln.n, qbuf, D_MODEL, L.q_b, 1.f);
-      RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.q, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
+      if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.q, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+      else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.q, a, mt, D_MODEL / BN_STORE, M, D_MODEL)));
       GemmArgs k;
       memset(&k, 0, sizeof(k));
       k.M = B;
@@ -1029,7 +1047,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     KLAUNCH(launch_kernel(attention_kernel, dim3(B * N_HEADS), dim3(64), 0, st, e->pdl, at));
     {
       GemmArgs a = dense_args(M, D_MODEL, ln.ctx, r, D_MODEL, L.wo_b, 1.f);
-      RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+      if (M >= BIG_M) RC((gemm<G_RESID, 128>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+      else RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
     }
     // ---- convolution module
     RC(run_norm(e, ln, st, r, nullptr, L.n_conv, ln.n, M));
@@ -1046,8 +1065,13 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       RC((gemm<G_GLU_DW, BN_GLU>(e, st, ln.m_n, L.pw1, a, (B + a.G - 1) / a.G, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
     } else {
       {
-        GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
-        RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+        if (M >= BIG_M) {
+          GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1w_b, 1.f);
+          RC((gemm<G_GLU, 128>(e, st, ln.m_n, L.pw1w, a, mt, 2 * D_MODEL / 128, M, D_MODEL)));
+        } else {
+          GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
+          RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+        }
       }
       DwArgs d;
       d.g = ln.g;
@@ -1058,11 +1082,12 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.bias = L.dw_b;
       d.e = ln.ebuf;
       d.T = Tl;
-      KLAUNCH(launch_kernel(dwconv_kernel, dim3(B, 2), dim3(96), 0, st, e->pdl, d));
+      KLAUNCH(launch_kernel(dwconv_kernel, dim3(B), dim3(DW_THREADS), 0, st, e->pdl, d));
     }
     {
       GemmArgs a = dense_args(M, D_MODEL, ln.ebuf, r, D_MODEL, L.pw2_b, 1.f);
-      RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+      if (M >= BIG_M) RC((gemm<G_RESID, 128>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+      else RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
     }
     // ---- second feed-forward, norm_out and what follows the layer
     RC(run_norm(e, ln, st, r, nullptr, L.n_ff2, ln.n, M));
@@ -1073,7 +1098,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
       GemmArgs a = dense_args(M2, D_FF, ln.m_red, ln.r_red, D_MODEL, e->red_pw_b, 1.f);
-      RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
+      if (M2 >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / 128, M2, D_MODEL, nullptr, 1, true)));
+      else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_mred, e->red_pw, a, (M2 + 127) / 128, D_MODEL / BN_STORE, M2, D_MODEL)));
       RC(run_norm(e, ln, st, ln.r_red, nullptr, e->L[7].n_ff1, ln.n, M2));
       RC(tap(1 + l, ln.r_red, M2));
     } else if (l == 14) {

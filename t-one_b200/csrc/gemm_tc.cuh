@@ -401,68 +401,72 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) PROF_MARK(1);   // prologue done
 
   if (warp == 0) {
+    // ---------------- TMA producer.  The first ring is filled by lanes 0..npre-1 in parallel (one stage per lane:
+    // issuing a TMA costs ~100+ cycles, and these loads sit on the critical path of a short-K GEMM); lane 0 then
+    // runs the steady-state loop.
+    int nvalid = 1;
+    if constexpr (KindTraits<KIND>::gather) {
+      nvalid = a.M - blockIdx.x * a.G;
+      nvalid = nvalid > a.G ? a.G : nvalid;
+    }
+    const uint32_t a_bytes = KindTraits<KIND>::gather ? (uint32_t)(nvalid * a.R * 128) : (uint32_t)Cfg::A_BYTES;
+    const int b_row = (KIND == G_CONV1) ? 0 : blockIdx.y * BN;
+    const int kz = (KIND == G_PARTIAL) ? blockIdx.z * a.nk * 64 : 0;   // first K element of this CTA's slice
+    const int npre = a.nk < STAGES ? a.nk : STAGES;
+    // The weight tiles do not depend on the previous kernel: put the first ring of them in flight, then wait for
+    // the predecessor grid before touching activations.
+    if (lane < npre) {
+      mbar_expect_tx(&full[lane], a_bytes + Cfg::B_BYTES);
+      tma_load_2d(sB + lane * Cfg::B_BYTES, &tmB, &full[lane], kz + lane * 64, b_row);
+    }
+    pdl_wait();
+    if (lane == 0) PROF_MARK(2);        // predecessor grid complete
+    // Gather tiles whose G streams sit in consecutive slots load all of them with ONE wide box per K step
+    // (tmAw: same view, box spans G slots); otherwise one box per stream.
+    bool wide = false;
+    int slot0 = 0;
+    if constexpr (KindTraits<KIND>::gather) {
+      slot0 = a.slots[blockIdx.x * a.G];
+      wide = (nvalid == a.G);
+      for (int g = 1; g < nvalid; ++g) wide = wide && (a.slots[blockIdx.x * a.G + g] == slot0 + g);
+    }
+    auto load_a = [&](int it, int s) {
+      uint8_t* dA = sA + s * Cfg::A_BYTES;
+      if constexpr (KIND == G_CONV0) {
+        // K iteration = kernel row kt; box = 64 mel bins x R frames starting at feature row kt
+        if (wide) tma_load_3d(dA, &tmAw, &full[s], 0, it, slot0);
+        else
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], 0, it, a.slots[blockIdx.x * a.G + g]);
+      } else if constexpr (KIND == G_CONV1) {
+        // K iteration = (kt, 64-wide piece kc of the 12-position x 32-channel window at f0 = 2*blockIdx.y).
+        // x1 is viewed as [slot][row triple][row in triple][44*32]; output frame t reads row 3t + kt, so the
+        // box walks R consecutive triples starting at kt/3 with the in-triple row fixed to kt%3.
+        const int kt = it / 6, kc = it - kt * 6;
+        if (wide) tma_load_4d(dA, &tmAw, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3, slot0);
+        else
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_4d(dA + g * a.R * 128, &tmA, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3,
+                        a.slots[blockIdx.x * a.G + g]);
+      } else if constexpr (KIND == G_KV) {
+        if (wide) tma_load_3d(dA, &tmAw, &full[s], it * 64, 0, slot0);
+        else
+          for (int g = 0; g < nvalid; ++g)
+            tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
+      } else {
+        tma_load_2d(dA, &tmA, &full[s], kz + it * 64, (KIND == G_GLU_DW) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
+      }
+    };
+    if (lane < npre) load_a(lane, lane);
+    __syncwarp();
     if (lane == 0) {
-      // ---------------- TMA producer
-      int nvalid = 1;
-      if constexpr (KindTraits<KIND>::gather) {
-        nvalid = a.M - blockIdx.x * a.G;
-        nvalid = nvalid > a.G ? a.G : nvalid;
-      }
-      const uint32_t a_bytes = KindTraits<KIND>::gather ? (uint32_t)(nvalid * a.R * 128) : (uint32_t)Cfg::A_BYTES;
-      const int b_row = (KIND == G_CONV1) ? 0 : blockIdx.y * BN;
-      const int kz = (KIND == G_PARTIAL) ? blockIdx.z * a.nk * 64 : 0;   // first K element of this CTA's slice
-      // The weight tiles do not depend on the previous kernel: put the first ring of them in flight, then wait for
-      // the predecessor grid before touching activations.
-      const int npre = a.nk < STAGES ? a.nk : STAGES;
-      for (int it = 0; it < npre; ++it) {
-        mbar_expect_tx(&full[it], a_bytes + Cfg::B_BYTES);
-        tma_load_2d(sB + it * Cfg::B_BYTES, &tmB, &full[it], kz + it * 64, b_row);
-      }
-      pdl_wait();
-      PROF_MARK(2);                     // predecessor grid complete
-      // Gather tiles whose G streams sit in consecutive slots load all of them with ONE wide box per K step
-      // (tmAw: same view, box spans G slots); otherwise one box per stream.
-      bool wide = false;
-      int slot0 = 0;
-      if constexpr (KindTraits<KIND>::gather) {
-        slot0 = a.slots[blockIdx.x * a.G];
-        wide = (nvalid == a.G);
-        for (int g = 1; g < nvalid; ++g) wide = wide && (a.slots[blockIdx.x * a.G + g] == slot0 + g);
-      }
-      for (int it = 0; it < a.nk; ++it) {
+      for (int it = npre; it < a.nk; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        if (it >= npre) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
-          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], kz + it * 64, b_row);
-        }
-        uint8_t* dA = sA + s * Cfg::A_BYTES;
-        if constexpr (KIND == G_CONV0) {
-          // K iteration = kernel row kt; box = 64 mel bins x R frames starting at feature row kt
-          if (wide) tma_load_3d(dA, &tmAw, &full[s], 0, it, slot0);
-          else
-            for (int g = 0; g < nvalid; ++g)
-              tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], 0, it, a.slots[blockIdx.x * a.G + g]);
-        } else if constexpr (KIND == G_CONV1) {
-          // K iteration = (kt, 64-wide piece kc of the 12-position x 32-channel window at f0 = 2*blockIdx.y).
-          // x1 is viewed as [slot][row triple][row in triple][44*32]; output frame t reads row 3t + kt, so the
-          // box walks R consecutive triples starting at kt/3 with the in-triple row fixed to kt%3.
-          const int kt = it / 6, kc = it - kt * 6;
-          if (wide) tma_load_4d(dA, &tmAw, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3, slot0);
-          else
-            for (int g = 0; g < nvalid; ++g)
-              tma_load_4d(dA + g * a.R * 128, &tmA, &full[s], blockIdx.y * 64 + kc * 64, kt % 3, kt / 3,
-                          a.slots[blockIdx.x * a.G + g]);
-        } else if constexpr (KIND == G_KV) {
-          if (wide) tma_load_3d(dA, &tmAw, &full[s], it * 64, 0, slot0);
-          else
-            for (int g = 0; g < nvalid; ++g)
-              tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
-        } else {
-          tma_load_2d(dA, &tmA, &full[s], kz + it * 64,
-                      (KIND == G_GLU_DW) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
-        }
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
+        tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], kz + it * 64, b_row);
+        load_a(it, s);
       }
     }
   } else if (warp == 1) {

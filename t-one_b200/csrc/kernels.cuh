@@ -536,52 +536,78 @@ struct DwArgs {
   int T;
 };
 
-__global__ void __launch_bounds__(96) dwconv_kernel(const DwArgs a) {
+// One CTA per stream, 192 threads.  The [30 cached | T new] x 384 tile is staged in shared memory with 16-byte
+// coalesced loads (all in flight at once); thread c then owns channels 2c, 2c+1: taps in registers, inputs streamed
+// from smem.  The new cache is rows [T, T+30) of the tile, copied back with coalesced 16-byte stores.
+constexpr int DW_THREADS = 192;
+constexpr int DW_ROWS = CONV_S + MAX_T;          // 43
+constexpr int DW_RV = D_MODEL / 8;               // uint4 per row
+
+__global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
+  __shared__ __align__(16) bf16 tile[DW_ROWS][D_MODEL];
   PROF_DECL();
   PROF_BEGIN(5);
   pdl_launch_dependents();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int T = a.T;
+  // BN-folded taps of this thread's two channels: weights, fetched before the PDL wait
+  float2 w[CONV_S + 1];
+#pragma unroll
+  for (int j = 0; j <= CONV_S; ++j) w[j] = __ldg(reinterpret_cast<const float2*>(a.w + j * D_MODEL + 2 * tid));
+  const float2 bb = __ldg(reinterpret_cast<const float2*>(a.bias + 2 * tid));
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
-  const int b = blockIdx.x;
-  const int c = (blockIdx.y * 96 + threadIdx.x) * 2;         // two adjacent channels per thread
-  const int T = a.T;
   bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride;
-  float2 col[CONV_S + MAX_T];
+  {
+    const uint4* c4 = reinterpret_cast<const uint4*>(cache);
+    const uint4* g4 = reinterpret_cast<const uint4*>(a.g + (size_t)b * T * D_MODEL);
+    uint4* t4 = reinterpret_cast<uint4*>(&tile[0][0]);
+    const int n_cache = CONV_S * DW_RV, n_all = (CONV_S + T) * DW_RV;
+    uint4 tmp[11];
 #pragma unroll
-  for (int i = 0; i < CONV_S; ++i)
-    col[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(cache + i * D_MODEL + c));
+    for (int k = 0; k < 11; ++k) {
+      const int i = tid + k * DW_THREADS;
+      if (i < n_all) tmp[k] = (i < n_cache) ? c4[i] : g4[i - n_cache];
+    }
 #pragma unroll
-  for (int t = 0; t < MAX_T; ++t)
-    if (t < T)
-      col[CONV_S + t] =
-          __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.g + (size_t)(b * T + t) * D_MODEL + c));
+    for (int k = 0; k < 11; ++k) {
+      const int i = tid + k * DW_THREADS;
+      if (i < n_all) t4[i] = tmp[k];
+    }
+  }
+  __syncthreads();
+  // y[t] = b' + sum_j w'[j] x[t + j]  (submodules.py:364-402 with BatchNorm folded), input-stationary order
   float2 acc[MAX_T];
-  const float2 bb = *reinterpret_cast<const float2*>(a.bias + c);
 #pragma unroll
   for (int t = 0; t < MAX_T; ++t) acc[t] = bb;
 #pragma unroll
-  for (int j = 0; j <= CONV_S; ++j) {
-    const float2 wj = *reinterpret_cast<const float2*>(a.w + j * D_MODEL + c);
+  for (int i = 0; i < DW_ROWS; ++i) {
+    if (i < CONV_S + T) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tile[i][2 * tid]));
 #pragma unroll
-    for (int t = 0; t < MAX_T; ++t)
-      if (t < T) {
-        acc[t].x = fmaf(wj.x, col[t + j].x, acc[t].x);
-        acc[t].y = fmaf(wj.y, col[t + j].y, acc[t].y);
+      for (int t = 0; t < MAX_T; ++t) {
+        const int j = i - t;                     // compile-time after unrolling
+        if (j >= 0 && j <= CONV_S && t < T) {
+          acc[t].x = fmaf(w[j].x, x.x, acc[t].x);
+          acc[t].y = fmaf(w[j].y, x.y, acc[t].y);
+        }
       }
+    }
   }
 #pragma unroll
   for (int t = 0; t < MAX_T; ++t)
     if (t < T)
-      *reinterpret_cast<__nv_bfloat162*>(a.e + (size_t)(b * T + t) * D_MODEL + c) =
+      *reinterpret_cast<__nv_bfloat162*>(a.e + (size_t)(b * T + t) * D_MODEL + 2 * tid) =
           __floats2bfloat162_rn(silu_f(acc[t].x), silu_f(acc[t].y));
-  // new cache = last 30 columns of [cache | g]  (submodules.py:364-370)
+  // new cache = last 30 rows of [cache | g]
+  {
+    uint4* c4 = reinterpret_cast<uint4*>(cache);
+    const uint4* t4 = reinterpret_cast<const uint4*>(&tile[T][0]);
 #pragma unroll
-  for (int i = 0; i < CONV_S; ++i) {
-    float2 vsel = col[i];
-#pragma unroll
-    for (int t = 1; t <= MAX_T; ++t)
-      if (t == T) vsel = col[i + t];
-    *reinterpret_cast<__nv_bfloat162*>(cache + i * D_MODEL + c) = __floats2bfloat162_rn(vsel.x, vsel.y);
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * DW_THREADS;
+      if (i < CONV_S * DW_RV) c4[i] = t4[i];
+    }
   }
   PROF_END();
 }
