@@ -144,8 +144,9 @@ struct tone_engine {
   // the captured graph): at small batch the step is bound by kernel-to-kernel latency, not by the SMs.
   struct Lane {
     float *r_full, *r_red, *qkv, *P, *part;
-    bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red;
-    CUtensorMap m_n, m_h, m_ctx, m_e, m_c1, m_mred;
+    bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red, *rb;
+    float* ss;                          // [rows][12] per-N-tile sums of squares of the residual rows (row-scale RMSNorm)
+    CUtensorMap m_n, m_h, m_ctx, m_e, m_c1, m_mred, m_rb;
     cudaStream_t stream = nullptr;       // lanes > 0 run on their own stream between fork and join
     cudaEvent_t done = nullptr;
     // view of the sub-batch this lane is working on (set per step)
@@ -344,6 +345,8 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
     rc |= dev_alloc(e, &ln.ebuf, R * D_MODEL);
     rc |= dev_alloc(e, &ln.c1, R * SUB_OUT);
     rc |= dev_alloc(e, &ln.m_red, R * D_FF);
+    rc |= dev_alloc(e, &ln.rb, R * D_MODEL);
+    rc |= dev_alloc(e, &ln.ss, R * 12);
     if (rc) return rc;
     if (li > 0) {
       CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -388,6 +391,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
     if ((rc = make_map_2d(e, &ln.m_e, ln.ebuf, R, D_MODEL, 128, false))) return rc;
     if ((rc = make_map_2d(e, &ln.m_c1, ln.c1, R, SUB_OUT, 128, false))) return rc;
     if ((rc = make_map_2d(e, &ln.m_mred, ln.m_red, R, D_FF, 128, false))) return rc;
+    if ((rc = make_map_2d(e, &ln.m_rb, ln.rb, R, D_MODEL, 128, false))) return rc;
   }
 
   CK((configure_gemm_tc<G_SWIGLU, BN_SWIGLU>()));
@@ -650,7 +654,16 @@ static int finalize_layer(tone_engine* e, int l) {
     NEEDW(b2, ff + "linear2.bias");
     if ((rc = expect_shape(w1, "linear1.weight", {D_FF, D_MODEL}))) return rc;
     if ((rc = expect_shape(w2, "linear2.weight", {D_MODEL, D_FF}))) return rc;
-    std::vector<float> up = interleave_rows(w1->data, wv->data, D_FF, D_MODEL, BN_SWIGLU / 2);
+    std::vector<float> w1d = w1->data, wvd = wv->data;
+    if (k == 1) {   // second feed-forward: its RMSNorm gain is folded into the weight columns (row-scale RMSNorm)
+      NEEDW(gff2, Lp + "norm_feed_forward2.weight");
+      for (int n = 0; n < D_FF; ++n)
+        for (int c = 0; c < D_MODEL; ++c) {
+          w1d[(size_t)n * D_MODEL + c] *= gff2->data[c];
+          wvd[(size_t)n * D_MODEL + c] *= gff2->data[c];
+        }
+    }
+    std::vector<float> up = interleave_rows(w1d, wvd, D_FF, D_MODEL, BN_SWIGLU / 2);
     std::vector<float> upb = interleave_rows(b1->data, bv->data, D_FF, 1, BN_SWIGLU / 2);
     WeightMat* mu = k == 0 ? &L.ff1_up : &L.ff2_up;
     WeightMat* md = k == 0 ? &L.ff1_down : &L.ff2_down;
@@ -700,6 +713,14 @@ static int finalize_layer(tone_engine* e, int l) {
   {
     std::vector<float> a(p1->data.begin(), p1->data.begin() + (size_t)D_MODEL * D_MODEL);
     std::vector<float> b(p1->data.begin() + (size_t)D_MODEL * D_MODEL, p1->data.end());
+    {   // norm_conv gain folded into the input columns (row-scale RMSNorm)
+      NEEDW(gcv, Lp + "norm_conv.weight");
+      for (int n = 0; n < D_MODEL; ++n)
+        for (int c = 0; c < D_MODEL; ++c) {
+          a[(size_t)n * D_MODEL + c] *= gcv->data[c];
+          b[(size_t)n * D_MODEL + c] *= gcv->data[c];
+        }
+    }
     std::vector<float> ab(p1b->data.begin(), p1b->data.begin() + D_MODEL);
     std::vector<float> bb(p1b->data.begin() + D_MODEL, p1b->data.end());
     if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, BN_GLU / 2), 2 * D_MODEL, D_MODEL, BN_GLU, &L.pw1)))
@@ -867,10 +888,16 @@ static int run_norm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, floa
 // Feed-forward: h = silu(n W1^T + b1) * (n Wv^T + bv); the down projection runs split-K and leaves its partial
 // sums in ln.part; the NEXT norm kernel adds 0.5 * (sum + b2) to the residual stream (conformer_blocks.py:814,834).
 static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const WeightMat& up, const float* up_b, const WeightMat& down,
-                  const float* down_b, PartIn* out) {
+                  const float* down_b, PartIn* out, int ss_tiles = 0) {
   const int mt = (M + 127) / 128;
-  GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.h, D_FF, up_b, 1.f);
-  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ln.m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+  // ss_tiles > 0: the input is the un-normalised residual in bf16 (ln.rb) with its row sums of squares in ln.ss
+  GemmArgs a = dense_args(M, D_MODEL, ss_tiles ? ln.rb : ln.n, ln.h, D_FF, up_b, 1.f);
+  if (ss_tiles) {
+    a.ss = ln.ss;
+    a.ss_ld = 12;
+    a.ss_tiles = ss_tiles;
+  }
+  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ss_tiles ? ln.m_rb : ln.m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
   int splits = 1;
   while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
   if (const char* v = getenv("TONE_SPLITK")) splits = atoi(v);
@@ -883,6 +910,32 @@ static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M,
   out->stride = b.z_stride;
   out->bias = down_b;
   out->scale = 0.5f;
+  return 0;
+}
+
+// r += A W^T + b through the tensor cores; also emits bf16(r) and the per-tile row sums of squares that let the next
+// GEMM apply the following RMSNorm as a row scale.  Returns the number of ss tiles through *ss_tiles.
+static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const bf16* A,
+                              const CUtensorMap& mapA, const WeightMat& w, const float* bias, float* r, int* ss_tiles) {
+  const int mt = (M + 127) / 128;
+  GemmArgs a = dense_args(M, D_MODEL, A, r, D_MODEL, bias, 1.f);
+  if (e->cfg.gemm_impl == 0) {
+    a.rb_out = ln.rb;
+    a.ss_out = ln.ss;
+    a.ss_ld = 12;
+    if (M >= BIG_M) {
+      *ss_tiles = D_MODEL / 128;
+      RC((gemm<G_RESID, 128>(e, st, mapA, w, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
+    } else {
+      *ss_tiles = D_MODEL / BN_RESID;
+      RC((gemm<G_RESID, BN_RESID>(e, st, mapA, w, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+    }
+  } else {   // SIMT debug path: plain residual GEMM, then one helper kernel for rb / ss
+    RC((gemm<G_RESID, BN_RESID>(e, st, mapA, w, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
+    rowscale_ref_kernel<<<(M + 127) / 128, 128, 0, st>>>(r, ln.rb, ln.ss, 12, M);
+    e->launches++;
+    *ss_tiles = 1;
+  }
   return 0;
 }
 
@@ -1045,16 +1098,15 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.mask_mode = (l == 14) ? 2 : 1;
     }
     KLAUNCH(launch_kernel(attention_kernel, dim3(B * N_HEADS), dim3(64), 0, st, e->pdl, at));
-    {
-      GemmArgs a = dense_args(M, D_MODEL, ln.ctx, r, D_MODEL, L.wo_b, 1.f);
-      if (M >= BIG_M) RC((gemm<G_RESID, 128>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
-      else RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_ctx, L.wo, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
-    }
-    // ---- convolution module
-    RC(run_norm(e, ln, st, r, nullptr, L.n_conv, ln.n, M));
+    int ss_tiles = 0;
+    RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));
+    // ---- convolution module: norm_conv is applied as a row scale inside the pointwise-conv GEMM (A = bf16(r))
     if (e->cfg.gemm_impl == 0 && e->fuse_dw) {
       // pointwise conv 1 + GLU + causal depthwise conv + BN + SiLU + cache roll in ONE kernel: tiles hold whole streams
-      GemmArgs a = dense_args(B, D_MODEL, ln.n, ln.ebuf, D_MODEL, L.pw1_b, 1.f);
+      GemmArgs a = dense_args(B, D_MODEL, ln.rb, ln.ebuf, D_MODEL, L.pw1_b, 1.f);
+      a.ss = ln.ss;
+      a.ss_ld = 12;
+      a.ss_tiles = ss_tiles;
       a.R = Tl;
       a.G = std::min(128 / Tl, 12);      // whole streams per tile; each epilogue warp keeps 3 cache columns in registers
       a.slots = ln.slots;
@@ -1062,16 +1114,15 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       a.dw_cache_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
       a.dw_w = L.dw_w;
       a.dw_b = L.dw_b;
-      RC((gemm<G_GLU_DW, BN_GLU>(e, st, ln.m_n, L.pw1, a, (B + a.G - 1) / a.G, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
+      RC((gemm<G_GLU_DW, BN_GLU>(e, st, ln.m_rb, L.pw1, a, (B + a.G - 1) / a.G, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
     } else {
       {
-        if (M >= BIG_M) {
-          GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1w_b, 1.f);
-          RC((gemm<G_GLU, 128>(e, st, ln.m_n, L.pw1w, a, mt, 2 * D_MODEL / 128, M, D_MODEL)));
-        } else {
-          GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.g, D_MODEL, L.pw1_b, 1.f);
-          RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_n, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
-        }
+        GemmArgs a = dense_args(M, D_MODEL, ln.rb, ln.g, D_MODEL, M >= BIG_M ? L.pw1w_b : L.pw1_b, 1.f);
+        a.ss = ln.ss;
+        a.ss_ld = 12;
+        a.ss_tiles = ss_tiles;
+        if (M >= BIG_M) RC((gemm<G_GLU, 128>(e, st, ln.m_rb, L.pw1w, a, mt, 2 * D_MODEL / 128, M, D_MODEL)));
+        else RC((gemm<G_GLU, BN_GLU>(e, st, ln.m_rb, L.pw1, a, mt, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
       }
       DwArgs d;
       d.g = ln.g;
@@ -1084,14 +1135,9 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.T = Tl;
       KLAUNCH(launch_kernel(dwconv_kernel, dim3(B), dim3(DW_THREADS), 0, st, e->pdl, d));
     }
-    {
-      GemmArgs a = dense_args(M, D_MODEL, ln.ebuf, r, D_MODEL, L.pw2_b, 1.f);
-      if (M >= BIG_M) RC((gemm<G_RESID, 128>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
-      else RC((gemm<G_RESID, BN_RESID>(e, st, ln.m_e, L.pw2, a, mt, D_MODEL / BN_RESID, M, D_MODEL)));
-    }
-    // ---- second feed-forward, norm_out and what follows the layer
-    RC(run_norm(e, ln, st, r, nullptr, L.n_ff2, ln.n, M));
-    RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff));
+    RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles));
+    // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer
+    RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff, ss_tiles));
     if (l == 6) {
       RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{ln.r_full, e->st_red, ln.slots, e->red_dw_w, e->red_dw_b, ln.m_red, T, T2};

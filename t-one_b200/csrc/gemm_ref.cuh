@@ -75,8 +75,14 @@ __global__ void gemm_ref_kernel(const GemmArgs a, int n_out) {
     constexpr int HW = BN / 2;               // packed tiles: [HW gate|a rows][HW value|b rows]
     const int tile = col / HW, c = col % HW;
     const int r0 = tile * BN + c, r1 = r0 + HW;
-    float x = ref_dot<KIND>(a, b, j, 0, r0) + a.bias[r0];
-    float y = ref_dot<KIND>(a, b, j, 0, r1) + a.bias[r1];
+    float rs = 1.f;
+    if (a.ss) {   // row-scale RMSNorm folded around the GEMM (see GemmArgs)
+      float t = 0.f;
+      for (int k = 0; k < a.ss_tiles; ++k) t += a.ss[(long long)row * a.ss_ld + k];
+      rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
+    }
+    float x = ref_dot<KIND>(a, b, j, 0, r0) * rs + a.bias[r0];
+    float y = ref_dot<KIND>(a, b, j, 0, r1) * rs + a.bias[r1];
     float o = (KIND == G_SWIGLU) ? silu_f(x) * y : x * sigmoid_f(y);
     reinterpret_cast<bf16*>(a.out)[(long long)row * a.ldo + col] = __float2bfloat16(o);
   } else if constexpr (KIND == G_CONV0) {
@@ -117,6 +123,19 @@ __global__ void decoder_ref_kernel(const GemmArgs a) {
     a.aux[row * 2] = lg[33] - lse;
     a.aux[row * 2 + 1] = lg[34] - lse;
   }
+}
+
+// Debug-path producer side of the row-scale RMSNorm: rb = bf16(r), ss[row][0] = sum of squares (one "tile").
+__global__ void rowscale_ref_kernel(const float* r, bf16* rb, float* ss, int ss_ld, int M) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float t = 0.f;
+  for (int c = 0; c < 384; ++c) {
+    const float v = r[(long long)row * 384 + c];
+    rb[(long long)row * 384 + c] = __float2bfloat16(v);
+    t += v * v;
+  }
+  ss[(long long)row * ss_ld] = t;
 }
 
 template <int KIND, int BN>

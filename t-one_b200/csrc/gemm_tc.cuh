@@ -46,6 +46,15 @@ struct GemmArgs {
   int* tokens;                // G_DECODER: argmax per frame
   float* aux;                 // G_DECODER: [rows][2] = logprob of ' ' (33) and of blank (34), what the phrase splitter needs
   long long z_stride;         // G_PARTIAL: elements between the partial outputs of consecutive K slices
+  // Row-scale form of RMSNorm (x g / (rms + eps)) folded around a GEMM: the PRODUCER (G_RESID) also emits the new
+  // residual row in bf16 (rb_out) and, per N tile, the sum of squares of its columns (ss_out[row][tile]); the
+  // CONSUMER (G_GLU / G_SWIGLU) reads A = rb, has the norm gain folded into its weights, and scales the accumulator
+  // row by 1 / (sqrt(sum_tiles ss) * d^-1/2 + eps).  Removes the RMSNorm kernel between the two GEMMs.
+  bf16* rb_out;
+  float* ss_out;
+  int ss_ld;                  // floats per row of ss (= number of N tiles of the producer)
+  const float* ss;            // consumer side: nullable
+  int ss_tiles;
   // G_GLU_DW: depthwise stage
   bf16* dw_cache;             // [slots][16][30][384], layer offset applied
   long long dw_cache_stride;  // elements between slots
@@ -214,6 +223,19 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
       }
     }
+    // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
+    float rs = 1.f;
+    if constexpr (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) {
+      if (a.ss) {
+        const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
+        if (rme.valid) {
+          const float* sp = a.ss + rme.out_row * a.ss_ld;
+          float t = 0.f;
+          for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
+          rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);   // 384^-1/2, eps outside the sqrt (submodules.py:50-52)
+        }
+      }
+    }
     // G_GLU_DW: the cached depthwise columns of this warp's (up to 3) streams are fetched while the main loop runs
     float dwc[KIND == G_GLU_DW ? 3 : 1][KIND == G_GLU_DW ? 30 : 1];
     if constexpr (KIND == G_GLU_DW) {
@@ -266,7 +288,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         float r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float x = acc[c + i] + gb[i], y = acc[HW + c + i] + ub[i];
+          const float x = fmaf(acc[c + i], rs, gb[i]), y = fmaf(acc[HW + c + i], rs, ub[i]);
           r[i] = (KIND == G_SWIGLU) ? silu_f(x) * y : x * sigmoid_f(y);
         }
         sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
@@ -341,9 +363,10 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
     for (int it = 0; it < 32 / O::RPI; ++it) {
       const int row = q * 32 + it * O::RPI + sub_row;
       const RowInfo ri = row_info<KIND>(a, row);
-      if (ri.valid) {
-        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-        if constexpr (KIND == G_RESID) {
+      if constexpr (KIND == G_RESID) {
+        float sq = 0.f;
+        if (ri.valid) {
+          char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
           const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
           float4 o = rres[it];
           o.x += d.x;
@@ -351,7 +374,20 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
           o.z += d.z;
           o.w += d.w;
           *reinterpret_cast<float4*>(dst) = o;
-        } else {
+          if (a.rb_out) {
+            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
+                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+          }
+        }
+        if (a.rb_out) {   // warp-uniform: reduce the row's LPR lanes, lane 0 of each row group stores the tile's sum
+#pragma unroll
+          for (int off = O::LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+          if (ri.valid && (lane % O::LPR) == 0) a.ss_out[ri.out_row * a.ss_ld + blockIdx.y] = sq;
+        }
+      } else if (ri.valid) {
+        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
+        {
           *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
         }
       }
