@@ -29,6 +29,7 @@
 #include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "encoder_cluster.cuh"
 
 using namespace tone;
 
@@ -90,8 +91,8 @@ struct WeightMat {      // a bf16 [N][K] matrix on the device with its TMA map (
 };
 
 struct LayerW {
-  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw1w, pw2;   // pw1w: pw1 packed for 128-wide tiles
-  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw1w_b, *pw2_b;
+  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw1w, pw1c, pw2;   // pw1w: pw1 packed for 128-wide tiles
+  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw1w_b, *pw1c_b, *pw2_b;   // pw1c: per-CTA [a 48 | b 48] blocks (cluster path)
   float *n_ff1, *n_att, *n_conv, *n_ff2, *n_out;
   float *qln_w, *qln_b, *kln_w, *kln_b;
   float *dw_w, *dw_b;
@@ -172,6 +173,16 @@ struct tone_engine {
   // (19.9 us vs 3.8 + 7.0 us): four epilogue warps per CTA cannot keep enough cache-column loads in flight.
   bool fuse_dw = false;
   int num_sms = 148;
+
+  // latency path: the 16 layers + decoder as one thread-block-cluster kernel (encoder_cluster.cuh)
+  bool cluster_ok = false;        // built and launchable on this device
+  int cluster_max_batch = 128;    // batches up to this size take the cluster path (TONE_CLUSTER_MAX_B)
+  int cluster_max_active = 0;     // co-resident clusters (occupancy query)
+  int cluster_G = 4;              // streams per cluster
+  CUtensorMap* d_cl_maps = nullptr;
+  ClParams* d_clp = nullptr;
+  float* d_taps = nullptr;        // debug: [17][rows_alloc][384]
+  unsigned long long* d_cl_prof = nullptr;   // TONE_CL_PROF=1: in-kernel timeline of cluster 0 / CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -728,6 +739,8 @@ static int finalize_layer(tone_engine* e, int l) {
     if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, BN_GLU / 2), &L.pw1_b))) return rc;
     if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, 64), 2 * D_MODEL, D_MODEL, 128, &L.pw1w))) return rc;
     if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, 64), &L.pw1w_b))) return rc;
+    if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, 48), 2 * D_MODEL, D_MODEL, 96, &L.pw1c))) return rc;
+    if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, 48), &L.pw1c_b))) return rc;
   }
   NEEDW(dw, Cp + "depthwise_conv.conv.weight");
   NEEDW(dwb, Cp + "depthwise_conv.conv.bias");
@@ -744,6 +757,166 @@ static int finalize_layer(tone_engine* e, int l) {
   NEEDW(p2b, Cp + "pointwise_conv2.bias");
   if ((rc = upload_mat(e, p2->data, D_MODEL, D_MODEL, BN_RESID, &L.pw2))) return rc;
   if ((rc = upload_f32(e, p2b->data, &L.pw2_b))) return rc;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ cluster (latency) path
+template <int T_, int G_>
+static cudaError_t launch_cluster_t(cudaStream_t st, int n_clusters, const ClParams* dp, const ClStep& step) {
+  using Cfg = ClCfg<T_, G_>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_clusters * CL_CTAS);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL_CTAS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, encoder_cluster_kernel<T_, G_>, dp, step);
+}
+
+template <int T_, int G_>
+static int configure_cluster_t(tone_engine* e) {
+  using Cfg = ClCfg<T_, G_>;
+  CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CL_CTAS * 64);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL_CTAS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  CK(cudaOccupancyMaxActiveClusters(&nc, encoder_cluster_kernel<T_, G_>, &cfg));
+  e->cluster_max_active = nc;
+  e->cluster_G = G_;
+  return 0;
+}
+
+static int finalize_cluster(tone_engine* e) {
+  if (const char* v = getenv("TONE_CLUSTER_MAX_B")) e->cluster_max_batch = atoi(v);
+  if (e->cfg.gemm_impl != 0) e->cluster_max_batch = 0;
+  int rc;
+  std::vector<CUtensorMap> maps(CG_TOTAL);
+  auto wm = [&](int idx, const WeightMat& w, int box_rows) -> int {
+    return make_map_2d(e, &maps[idx], w.ptr, w.N, w.K, box_rows, true);
+  };
+  for (int l = 0; l < N_LAYERS; ++l) {
+    LayerW& L = e->L[l];
+    const int b = l * CM_PER_LAYER;
+    if ((rc = wm(b + CM_FF1_UP, L.ff1_up, 192))) return rc;
+    if ((rc = wm(b + CM_FF1_DOWN, L.ff1_down, 192))) return rc;
+    if ((rc = wm(b + CM_QKV, l < 14 ? L.qkv : L.q, 48))) return rc;
+    if ((rc = wm(b + CM_KV, l < 14 ? L.qkv : L.kv, 48))) return rc;
+    if ((rc = wm(b + CM_WO, L.wo, 192))) return rc;
+    if ((rc = wm(b + CM_PW1, L.pw1c, 96))) return rc;
+    if ((rc = wm(b + CM_PW2, L.pw2, 192))) return rc;
+    if ((rc = wm(b + CM_FF2_UP, L.ff2_up, 192))) return rc;
+    if ((rc = wm(b + CM_FF2_DOWN, L.ff2_down, 192))) return rc;
+  }
+  if ((rc = wm(CG_RED_PW, e->red_pw, 192))) return rc;
+  if ((rc = wm(CG_DEC, e->dec_w, 48))) return rc;
+  {
+    const uint64_t S = e->cfg.max_slots;
+    uint64_t d[3] = {D_MODEL, KV_ROWS_MAX, S}, s[2] = {D_MODEL * 2, (uint64_t)KV_ROWS_MAX * D_MODEL * 2};
+    uint32_t b14[3] = {64, MHSA_S / 2, 1}, b15[3] = {64, MHSA_S, 1};
+    if ((rc = make_map(e, &maps[CG_KVC14], e->st_kv14, 3, d, s, b14, false))) return rc;
+    if ((rc = make_map(e, &maps[CG_KVC15], e->st_kv15, 3, d, s, b15, false))) return rc;
+  }
+  rc = dev_alloc(e, &e->d_cl_maps, (size_t)CG_TOTAL);
+  if (rc) return rc;
+  CK(cudaMemcpy(e->d_cl_maps, maps.data(), sizeof(CUtensorMap) * CG_TOTAL, cudaMemcpyHostToDevice));
+  ClParams p;
+  memset(&p, 0, sizeof(p));
+  p.maps = e->d_cl_maps;
+  for (int l = 0; l < N_LAYERS; ++l) {
+    LayerW& L = e->L[l];
+    ClLayer& c = p.L[l];
+    c.ff1_up_b = L.ff1_up_b;
+    c.ff1_down_b = L.ff1_down_b;
+    c.ff2_up_b = L.ff2_up_b;
+    c.ff2_down_b = L.ff2_down_b;
+    c.qkv_b = L.qkv_b;
+    c.q_b = L.q_b;
+    c.kv_b = L.kv_b;
+    c.wo_b = L.wo_b;
+    c.pw1_b = L.pw1c_b;
+    c.pw2_b = L.pw2_b;
+    c.g_ff1 = L.n_ff1;
+    c.g_att = L.n_att;
+    c.g_out = L.n_out;
+    c.qln_w = L.qln_w;
+    c.qln_b = L.qln_b;
+    c.kln_w = L.kln_w;
+    c.kln_b = L.kln_b;
+    c.dw_w = L.dw_w;
+    c.dw_b = L.dw_b;
+  }
+  p.red_dw_w = e->red_dw_w;
+  p.red_dw_b = e->red_dw_b;
+  p.red_pw_b = e->red_pw_b;
+  p.dec_b = e->dec_b;
+  p.rope_cos = e->rope_cos;
+  p.rope_sin = e->rope_sin;
+  p.kv14 = e->st_kv14;
+  p.kv15 = e->st_kv15;
+  p.conv = e->st_conv;
+  p.red = e->st_red;
+  rc = dev_alloc(e, (char**)&e->d_clp, sizeof(ClParams));
+  if (rc) return rc;
+  CK(cudaMemcpy(e->d_clp, &p, sizeof(p), cudaMemcpyHostToDevice));
+  if (e->T == 10) rc = configure_cluster_t<10, 4>(e);
+  else rc = configure_cluster_t<13, 3>(e);
+  if (rc) return rc;
+  e->cluster_ok = e->cluster_max_active > 0;
+  if (getenv("TONE_CL_PROF") && atoi(getenv("TONE_CL_PROF"))) {
+    if ((rc = dev_alloc(e, &e->d_cl_prof, (size_t)6144))) return rc;
+  }
+  return 0;
+}
+
+// Diagnostics: timeline of the last cluster-kernel launch (TONE_CL_PROF=1) and the occupancy the driver reported.
+extern "C" int tone_cluster_prof_read(tone_engine* e, unsigned long long* out /* [6144] */, int32_t* max_active) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  if (max_active) *max_active = e->cluster_max_active;
+  if (out) {
+    if (!e->d_cl_prof) return fail(TONE_ESTATE, "TONE_CL_PROF was not set when the engine was created");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, e->d_cl_prof, 6144 * 8, cudaMemcpyDeviceToHost));
+  }
+  return TONE_OK;
+}
+
+static int run_cluster(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t st, float* d_taps) {
+  ClStep s;
+  memset(&s, 0, sizeof(s));
+  s.slots = ln.slots;
+  s.len_in = ln.len_in;
+  s.r_in = ln.r_full;
+  s.logprobs = ln.lp_out;
+  s.tokens = ln.tok_out;
+  s.aux = ln.aux_out;
+  s.taps = d_taps;
+  s.tap_stride = (long long)e->rows_alloc * D_MODEL;
+  s.B = B;
+  s.prof = e->d_cl_prof;
+  const int n_groups = (B + e->cluster_G - 1) / e->cluster_G;
+  const int nc = std::min(n_groups, e->cluster_max_active);
+  cudaError_t err = (e->T == 10) ? launch_cluster_t<10, 4>(st, nc, e->d_clp, s) : launch_cluster_t<13, 3>(st, nc, e->d_clp, s);
+  e->launches++;
+  if (err != cudaSuccess) return fail(TONE_ECUDA, "cluster kernel launch: %s", cudaGetErrorString(err));
   return 0;
 }
 
@@ -776,6 +949,7 @@ extern "C" int tone_finalize_weights(tone_engine* e) {
     if ((rc = upload_f32(e, db->data, &e->dec_b))) return rc;
   }
   e->host_w.clear();
+  if ((rc = finalize_cluster(e))) return rc;
   CK(cudaDeviceSynchronize());   // pageable H2D copies may still be in flight when cudaMemcpy returns
   e->finalized = true;
   return TONE_OK;
@@ -1017,6 +1191,19 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
   }
   RC(run_norm(e, ln, st, ln.r_full, e->out_norm_g, e->L[0].n_ff1, ln.n, M));
   RC(tap(0, ln.r_full, M));
+
+  if (e->cluster_ok && B <= e->cluster_max_batch) {
+    // latency path: layers 0..15 and the decoder in one cluster kernel
+    if (taps && !e->d_taps) RC(dev_alloc(e, &e->d_taps, (size_t)17 * e->rows_alloc * D_MODEL));
+    RC(run_cluster(e, ln, B, st, taps ? e->d_taps : nullptr));
+    if (taps) {
+      CK(cudaStreamSynchronize(st));
+      for (int l = 0; l < N_LAYERS; ++l)
+        CK(cudaMemcpy(taps + (size_t)(1 + l) * B * T * D_MODEL, e->d_taps + (size_t)(1 + l) * e->rows_alloc * D_MODEL,
+                      (size_t)B * T * D_MODEL * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
 
   for (int l = 0; l < N_LAYERS; ++l) {
     LayerW& L = e->L[l];
