@@ -176,9 +176,9 @@ struct tone_engine {
 
   // latency path: the 16 layers + decoder as one thread-block-cluster kernel (encoder_cluster.cuh)
   bool cluster_ok = false;        // built and launchable on this device
-  int cluster_max_batch = 128;    // batches up to this size take the cluster path (TONE_CLUSTER_MAX_B)
-  int cluster_max_active = 0;     // co-resident clusters (occupancy query)
-  int cluster_G = 4;              // streams per cluster
+  int cluster_max_batch = 0;      // batches up to this size take the cluster path (TONE_CLUSTER_MAX_B); 0 = off
+  int cluster_max_active[2] = {0, 0};   // co-resident clusters of the small-G / large-G instantiation (occupancy query)
+  int cluster_Gs[2] = {4, 5};           // streams per cluster: 4 | 5 at T = 10, 3 | 4 at T = 13
   CUtensorMap* d_cl_maps = nullptr;
   ClParams* d_clp = nullptr;
   float* d_taps = nullptr;        // debug: [17][rows_alloc][384]
@@ -781,7 +781,7 @@ static cudaError_t launch_cluster_t(cudaStream_t st, int n_clusters, const ClPar
 }
 
 template <int T_, int G_>
-static int configure_cluster_t(tone_engine* e) {
+static int configure_cluster_t(tone_engine* e, int which) {
   using Cfg = ClCfg<T_, G_>;
   CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -799,8 +799,8 @@ static int configure_cluster_t(tone_engine* e) {
   cfg.numAttrs = 1;
   int nc = 0;
   CK(cudaOccupancyMaxActiveClusters(&nc, encoder_cluster_kernel<T_, G_>, &cfg));
-  e->cluster_max_active = nc;
-  e->cluster_G = G_;
+  e->cluster_max_active[which] = nc;
+  e->cluster_Gs[which] = G_;
   return 0;
 }
 
@@ -815,17 +815,17 @@ static int finalize_cluster(tone_engine* e) {
   for (int l = 0; l < N_LAYERS; ++l) {
     LayerW& L = e->L[l];
     const int b = l * CM_PER_LAYER;
-    if ((rc = wm(b + CM_FF1_UP, L.ff1_up, 192))) return rc;
-    if ((rc = wm(b + CM_FF1_DOWN, L.ff1_down, 192))) return rc;
+    if ((rc = wm(b + CM_FF1_UP, L.ff1_up, 64))) return rc;
+    if ((rc = wm(b + CM_FF1_DOWN, L.ff1_down, 128))) return rc;
     if ((rc = wm(b + CM_QKV, l < 14 ? L.qkv : L.q, 48))) return rc;
     if ((rc = wm(b + CM_KV, l < 14 ? L.qkv : L.kv, 48))) return rc;
-    if ((rc = wm(b + CM_WO, L.wo, 192))) return rc;
+    if ((rc = wm(b + CM_WO, L.wo, 128))) return rc;
     if ((rc = wm(b + CM_PW1, L.pw1c, 96))) return rc;
-    if ((rc = wm(b + CM_PW2, L.pw2, 192))) return rc;
-    if ((rc = wm(b + CM_FF2_UP, L.ff2_up, 192))) return rc;
-    if ((rc = wm(b + CM_FF2_DOWN, L.ff2_down, 192))) return rc;
+    if ((rc = wm(b + CM_PW2, L.pw2, 128))) return rc;
+    if ((rc = wm(b + CM_FF2_UP, L.ff2_up, 64))) return rc;
+    if ((rc = wm(b + CM_FF2_DOWN, L.ff2_down, 128))) return rc;
   }
-  if ((rc = wm(CG_RED_PW, e->red_pw, 192))) return rc;
+  if ((rc = wm(CG_RED_PW, e->red_pw, 128))) return rc;
   if ((rc = wm(CG_DEC, e->dec_w, 48))) return rc;
   {
     const uint64_t S = e->cfg.max_slots;
@@ -876,10 +876,15 @@ static int finalize_cluster(tone_engine* e) {
   rc = dev_alloc(e, (char**)&e->d_clp, sizeof(ClParams));
   if (rc) return rc;
   CK(cudaMemcpy(e->d_clp, &p, sizeof(p), cudaMemcpyHostToDevice));
-  if (e->T == 10) rc = configure_cluster_t<10, 4>(e);
-  else rc = configure_cluster_t<13, 3>(e);
+  if (e->T == 10) {
+    if ((rc = configure_cluster_t<10, 4>(e, 0))) return rc;
+    rc = configure_cluster_t<10, 5>(e, 1);
+  } else {
+    if ((rc = configure_cluster_t<13, 3>(e, 0))) return rc;
+    rc = configure_cluster_t<13, 4>(e, 1);
+  }
   if (rc) return rc;
-  e->cluster_ok = e->cluster_max_active > 0;
+  e->cluster_ok = e->cluster_max_active[0] > 0 && e->cluster_max_active[1] > 0;
   if (getenv("TONE_CL_PROF") && atoi(getenv("TONE_CL_PROF"))) {
     if ((rc = dev_alloc(e, &e->d_cl_prof, (size_t)6144))) return rc;
   }
@@ -889,7 +894,7 @@ static int finalize_cluster(tone_engine* e) {
 // Diagnostics: timeline of the last cluster-kernel launch (TONE_CL_PROF=1) and the occupancy the driver reported.
 extern "C" int tone_cluster_prof_read(tone_engine* e, unsigned long long* out /* [6144] */, int32_t* max_active) {
   if (!e) return fail(TONE_EINVAL, "null engine");
-  if (max_active) *max_active = e->cluster_max_active;
+  if (max_active) *max_active = e->cluster_max_active[0] * 1000 + e->cluster_max_active[1];
   if (out) {
     if (!e->d_cl_prof) return fail(TONE_ESTATE, "TONE_CL_PROF was not set when the engine was created");
     CK(cudaSetDevice(e->cfg.device));
@@ -905,6 +910,7 @@ static int run_cluster(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_
   s.slots = ln.slots;
   s.len_in = ln.len_in;
   s.r_in = ln.r_full;
+  s.res = ln.r_red;
   s.logprobs = ln.lp_out;
   s.tokens = ln.tok_out;
   s.aux = ln.aux_out;
@@ -912,9 +918,14 @@ static int run_cluster(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_
   s.tap_stride = (long long)e->rows_alloc * D_MODEL;
   s.B = B;
   s.prof = e->d_cl_prof;
-  const int n_groups = (B + e->cluster_G - 1) / e->cluster_G;
-  const int nc = std::min(n_groups, e->cluster_max_active);
-  cudaError_t err = (e->T == 10) ? launch_cluster_t<10, 4>(st, nc, e->d_clp, s) : launch_cluster_t<13, 3>(st, nc, e->d_clp, s);
+  // the smaller group size if all groups are co-resident (one wave), else the larger one
+  int which = ((B + e->cluster_Gs[0] - 1) / e->cluster_Gs[0] <= e->cluster_max_active[0]) ? 0 : 1;
+  if (const char* v = getenv("TONE_CLUSTER_G")) which = atoi(v) == e->cluster_Gs[1] ? 1 : 0;
+  const int G = e->cluster_Gs[which];
+  const int nc = std::min((B + G - 1) / G, e->cluster_max_active[which]);
+  cudaError_t err;
+  if (e->T == 10) err = which ? launch_cluster_t<10, 5>(st, nc, e->d_clp, s) : launch_cluster_t<10, 4>(st, nc, e->d_clp, s);
+  else err = which ? launch_cluster_t<13, 4>(st, nc, e->d_clp, s) : launch_cluster_t<13, 3>(st, nc, e->d_clp, s);
   e->launches++;
   if (err != cudaSuccess) return fail(TONE_ECUDA, "cluster kernel launch: %s", cudaGetErrorString(err));
   return 0;
