@@ -42,6 +42,9 @@ typedef struct tone_config {
   int32_t max_batch;     /* largest B accepted by tone_step                                  */
   int32_t gemm_impl;     /* 0 = tcgen05/TMEM/TMA (product path), 1 = SIMT debug kernels      */
   int32_t use_graph;     /* 1 = replay a captured CUDA graph per batch size, 0 = eager       */
+  int32_t cluster_max_batch; /* experimental latency path: batches up to this size run the 16  */
+                         /* Conformer layers + decoder as ONE thread-block-cluster kernel     */
+                         /* (csrc/encoder_cluster.cuh); 0 = off (default)                    */
 } tone_config;
 
 /* Shapes a caller needs to size its buffers (tone/onnx_wrapper.py:30-34,
@@ -129,6 +132,11 @@ int tone_step_debug(tone_engine* e, int32_t B, const int32_t* slots, const int32
  * fp32, rounded on upload; fp32 result).  Used by the GPU unit tests. */
 int tone_selftest_gemm(tone_engine* e, int32_t M, int32_t N, int32_t K, const float* A, const float* W,
                        float* C, int32_t block_n);
+
+/* Debug: diagnostics of the experimental cluster (latency) path.  out (nullable): 6144 uint64 of in-kernel
+ * timestamps of the last cluster-kernel launch (needs TONE_CL_PROF=1 at tone_create); max_active (nullable):
+ * co-resident clusters reported by the occupancy query, small-group * 1000 + large-group instantiation. */
+int tone_cluster_prof_read(tone_engine* e, unsigned long long* out, int32_t* max_active);
 
 #ifdef __cplusplus
 }

@@ -805,6 +805,7 @@ static int configure_cluster_t(tone_engine* e, int which) {
 }
 
 static int finalize_cluster(tone_engine* e) {
+  e->cluster_max_batch = e->cfg.cluster_max_batch;
   if (const char* v = getenv("TONE_CLUSTER_MAX_B")) e->cluster_max_batch = atoi(v);
   if (e->cfg.gemm_impl != 0) e->cluster_max_batch = 0;
   int rc;

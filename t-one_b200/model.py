@@ -28,13 +28,14 @@ SYMBOLS = (
     "tone_create", "tone_destroy", "tone_get_info", "tone_last_error", "tone_load_weight",
     "tone_finalize_weights", "tone_alloc_slots", "tone_release_slots", "tone_reset_slots", "tone_step",
     "tone_stage", "tone_step_staged", "tone_fetch", "tone_fetch_greedy", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
-    "tone_import_state", "tone_step_debug", "tone_selftest_gemm",
+    "tone_import_state", "tone_step_debug", "tone_selftest_gemm", "tone_cluster_prof_read",
 )
 
 
 class ToneConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_samples", C.c_int32), ("max_slots", C.c_int32),
-                ("max_batch", C.c_int32), ("gemm_impl", C.c_int32), ("use_graph", C.c_int32)]
+                ("max_batch", C.c_int32), ("gemm_impl", C.c_int32), ("use_graph", C.c_int32),
+                ("cluster_max_batch", C.c_int32)]
 
 
 class ToneInfo(C.Structure):
@@ -115,10 +116,11 @@ class Engine:
     """One engine per GPU: weights, resident stream slots, step."""
 
     def __init__(self, weights=None, chunk_samples: int = 2400, max_slots: int = 64, max_batch: Optional[int] = None,
-                 device: int = 0, gemm_impl: int = 0, use_graph: bool = True):
+                 device: int = 0, gemm_impl: int = 0, use_graph: bool = True, cluster_max_batch: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
-        cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph))
+        cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph),
+                         int(cluster_max_batch))
         rc = self._lib.tone_create(C.byref(cfg), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

@@ -126,6 +126,49 @@ def test_step_matches_oracle(engines, weights, tb, C, B, n):
         eng.release_slots(slots)
 
 
+# ---- experimental cluster (latency) path: the 16 layers + decoder as one thread-block-cluster kernel
+@pytest.mark.parametrize("C,B,n,G", [(2400, 5, 5, None), (3200, 7, 4, None), (2400, 64, 3, None), (2400, 66, 2, "4"),
+                                     (2400, 78, 2, "5"), (3200, 50, 2, "3")])
+def test_cluster_path_matches_oracle(weights, tb, monkeypatch, C, B, n, G):
+    """Same parity bar as the per-kernel path.  Cases cover: a ragged last group (B not a multiple of the group size),
+    both group-size instantiations, and more groups than co-resident clusters (66 streams / 4 = 17 groups, 78 / 5 = 16,
+    50 / 3 = 17 against 15 clusters), where clusters loop over groups."""
+    if G is not None:
+        monkeypatch.setenv("TONE_CLUSTER_G", G)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=80, max_batch=80, cluster_max_batch=80)
+    try:
+        W = orc.to_torch(weights)
+        pcm = tb.synth.telephony_pcm(B, C * n, seed=300 + B)
+        slots = eng.alloc_slots(B)
+        lp, tk = _stream_engine(eng, slots, pcm, C)
+        assert eng._get_info().launches_per_step < 20       # the cluster kernel really ran
+        ref, st = _stream_oracle(W, pcm, C)
+        assert np.isfinite(lp).all()
+        assert np.abs(lp - ref).max() <= LP_TOL
+        _check_tokens(tk, ref)
+        assert (tk == lp.argmax(-1)).all()
+        _check_state(eng, slots, st)
+    finally:
+        eng.close()
+
+
+def test_cluster_path_agrees_with_kernel_path_over_many_chunks(weights, tb):
+    """Both device paths carry the same state layout: run 12 chunks on each (first three exercise the key masks) and
+    compare logprobs and the exported state directly."""
+    C, B, n = 2400, 9, 12
+    pcm = tb.synth.telephony_pcm(B, C * n, seed=77)
+    outs = []
+    for cmb in (0, 80):
+        eng = tb.Engine(weights, chunk_samples=C, max_slots=16, max_batch=16, cluster_max_batch=cmb)
+        slots = eng.alloc_slots(B)
+        lp, _ = _stream_engine(eng, slots, pcm, C)
+        st = np.stack([eng.export_state(int(s)).astype(np.float32) for s in slots])
+        outs.append((lp, st))
+        eng.close()
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= LP_TOL_EMU
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= ST_TOL
+
+
 def test_simt_debug_path_agrees(engines, tb):
     """The SIMT debug GEMMs and the tcgen05 GEMMs see the same packed operands: results agree tightly."""
     C, B = 2400, 3
