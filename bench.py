@@ -34,6 +34,17 @@ METRIC = "streaming RTFx (audio-sec/sec)"
 UNIT = "audio-s/s"
 
 
+def measured_traffic(streams: int, chunk: int):
+    """DRAM bytes of one step from the committed ncu capture (profiles/r01_dram_traffic_B64.json:
+    sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum).  Only quoted for the workload it was
+    measured on; ncu replays every launch with cold caches, so this is an upper bound of the live traffic."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_traffic_B64.json")
+    if streams == 64 and chunk == 2400 and os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["dram_total_bytes"])
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -253,8 +264,12 @@ def run_ours(args):
             "gpu_launches": launches * K,
             "launches_per_step": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
-                         "kernel": "whole step graph (one launch = one 64-stream step); per-kernel shares in profiles/"},
+                         "frac": achieved / peaks["tflops"], "traffic": measured_traffic(B, chunk),
+                         "traffic_note": "DRAM bytes per step launch, ncu cold-cache replay (profiles/r01_dram_traffic_B64.md); "
+                                         f"algorithmic: {eng.info.weight_bytes / 1e6:.0f} MB weights + {B * 889_916 / 1e6:.0f} MB state/io",
+                         "peak_source": peaks["src"],
+                         "kernel": f"whole step graph (one launch = one {B}-stream step, {launches} kernels); per-kernel shares, "
+                                   "ncu --set full of the GEMM kinds and the DRAM traffic in profiles/"},
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
