@@ -401,13 +401,26 @@ __device__ __forceinline__ void ln_rope_row(const float* src, const float* w, co
     const float4 t = *reinterpret_cast<const float4*>(src + i);
     x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w;
   }
-  float mean = 0.f;
+  // four partial sums: 12-long dependent chains instead of 48
+  float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < D_HEAD; ++i) mean += x[i];
-  mean *= (1.0f / D_HEAD);
-  float var = 0.f;
+  for (int i = 0; i < D_HEAD; i += 4) {
+    m4[0] += x[i];
+    m4[1] += x[i + 1];
+    m4[2] += x[i + 2];
+    m4[3] += x[i + 3];
+  }
+  const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.0f / D_HEAD);
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < D_HEAD; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+  for (int i = 0; i < D_HEAD; i += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = x[i + k] - mean;
+      v4[k] = fmaf(d, d, v4[k]);
+    }
+  }
+  const float var = (v4[0] + v4[1]) + (v4[2] + v4[3]);
   const float inv = rsqrtf(var * (1.0f / D_HEAD) + 1e-5f);   // nn.LayerNorm(48), submodules.py:200-201
 #pragma unroll
   for (int i = 0; i < D_HEAD; ++i) x[i] = (x[i] - mean) * inv * w[i] + bia[i];
@@ -422,104 +435,162 @@ __device__ __forceinline__ void ln_rope_row(const float* src, const float* w, co
   for (int i = 0; i < D_HEAD; ++i) dst[i] = x[i] * scale;
 }
 
-__global__ void __launch_bounds__(64) attention_kernel(const AttnArgs a) {
-  __shared__ float qs[MAX_T][D_HEAD];
-  __shared__ float ks[MHSA_S + MAX_T][D_HEAD + 1];
-  __shared__ float ps[MAX_T][MHSA_S + MAX_T + 1];
-  __shared__ __align__(16) float vs[MHSA_S + MAX_T][D_HEAD];
+// One CTA per STREAM, all 8 heads.
+//   RECOMPUTE (layers 0, 7, 14, 15; 512 threads): thread = (key row j, head) or (query row t, head): per-head LayerNorm
+//   + RoPE with the row in registers; query rows go to shared memory, key rows stay in registers and produce their
+//   column of the score matrix; one warp per (head, query) row does the masked softmax and publishes P for the
+//   score-sharing layers.
+//   all layers (384 threads in the score-sharing instantiation): thread = (head, dim) accumulates ctx[t] over the keys,
+//   reading V coalesced straight from global memory in batches of 8 keys (each V element is used by exactly one
+//   thread), P broadcast from shared memory.
+constexpr int ATT_THREADS_REC = 512;
+constexpr int ATT_THREADS = D_MODEL;       // 384
+constexpr int ATT_TK = MHSA_S + MAX_T;     // 43
+
+template <bool RECOMPUTE>
+__global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) attention_kernel(const AttnArgs a) {
+  constexpr int NT = RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS;
+  // query rows as [t][d / 4][head] float4: the 8 heads of a quarter-warp read 8 consecutive 16 B words (no conflicts)
+  __shared__ float4 qs[RECOMPUTE ? MAX_T : 1][D_HEAD / 4][N_HEADS];             // 20 KB (recompute only)
+  __shared__ __align__(16) float ps[N_HEADS][MAX_T][48];                        // 20 KB; columns >= Tk are zero in the P.V loop
   PROF_DECL();
   PROF_BEGIN(4);
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
-  const int b = blockIdx.x / N_HEADS, h = blockIdx.x - b * N_HEADS;
+  const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int T = a.T, Tk = a.Tk, S = a.S;
-  float* Pg = a.P + ((size_t)(b * N_HEADS + h) * T) * Tk;
-
-  // V tile [Tk][48] -> smem: 12 float4 per row, independent loads issued up front
-  {
-    float4 tmp[9];
-    const float* vp = a.v + (size_t)b * Tk * a.ldv + h * D_HEAD;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int idx = tid + i * 64;
-      if (idx < Tk * 12) tmp[i] = *reinterpret_cast<const float4*>(vp + (size_t)(idx / 12) * a.ldv + (idx % 12) * 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int idx = tid + i * 64;
-      if (idx < Tk * 12) *reinterpret_cast<float4*>(&vs[idx / 12][(idx % 12) * 4]) = tmp[i];
-    }
+  float* Pg = a.P + (size_t)b * N_HEADS * T * Tk;
+  const float* vcol = a.v + (size_t)b * Tk * a.ldv + tid;
+  // padding columns [Tk, Tk + 8) are read by the 8-wide P.V loop: keep them zero (all other phases touch j < Tk only)
+  for (int i = tid; i < N_HEADS * MAX_T * 8; i += NT) {
+    const int j = Tk + (i & 7);
+    if (j < 48) (&ps[0][0][0])[(i >> 3) * 48 + j] = 0.f;
   }
-  if (a.recompute) {
-    if (tid < T) {
-      ln_rope_row(a.q + (size_t)(b * T + tid) * a.ldq + h * D_HEAD, a.q_ln_w, a.q_ln_b,
-                  a.rope_cos + (tid + MHSA_S) * 16, a.rope_sin + (tid + MHSA_S) * 16,
-                  0.14433756729740643f /* 1/sqrt(48) */, qs[tid]);
-    } else if (tid < T + Tk) {
-      const int j = tid - T;                                   // key position j - S (submodules.py:136)
-      ln_rope_row(a.k + (size_t)(b * Tk + j) * a.ldk + h * D_HEAD, a.k_ln_w, a.k_ln_b,
-                  a.rope_cos + (j - S + MHSA_S) * 16, a.rope_sin + (j - S + MHSA_S) * 16, 1.0f, ks[j]);
+
+  if constexpr (RECOMPUTE) {
+    const int nk = Tk * N_HEADS, nq = T * N_HEADS;      // <= 344 + 104 <= 512
+    float kx[D_HEAD];
+    int kj = -1, kh = 0;
+    if (tid < nk) {
+      kj = tid / N_HEADS;
+      kh = tid - kj * N_HEADS;
+      ln_rope_row(a.k + (size_t)(b * Tk + kj) * a.ldk + kh * D_HEAD, a.k_ln_w, a.k_ln_b,
+                  a.rope_cos + (kj - S + MHSA_S) * 16, a.rope_sin + (kj - S + MHSA_S) * 16, 1.0f, kx);
+    } else if (tid < nk + nq) {
+      const int i = tid - nk, t = i / N_HEADS, h = i - t * N_HEADS;
+      float qx[D_HEAD];
+      ln_rope_row(a.q + (size_t)(b * T + t) * a.ldq + h * D_HEAD, a.q_ln_w, a.q_ln_b,
+                  a.rope_cos + (t + MHSA_S) * 16, a.rope_sin + (t + MHSA_S) * 16,
+                  0.14433756729740643f /* 1/sqrt(48) */, qx);
+#pragma unroll
+      for (int d = 0; d < D_HEAD; d += 4) qs[t][d >> 2][h] = make_float4(qx[d], qx[d + 1], qx[d + 2], qx[d + 3]);
     }
     __syncthreads();
+    if (threadIdx.x == 0) PROF_MARK(1);
     int off = 0;
     if (a.mask_mode == 1) off = MHSA_S - a.len_in[b];
     else if (a.mask_mode == 2) off = (MHSA_S - a.len_in[b]) / 2;
-    if (tid < Tk) {
-      float kr[D_HEAD];
-#pragma unroll
-      for (int d = 0; d < D_HEAD; ++d) kr[d] = ks[tid][d];
-      const bool masked = tid < off;                           // cache columns older than the stream
+    if (kj >= 0) {
+      const bool masked = kj < off;                              // cache columns older than the stream
       for (int t = 0; t < T; ++t) {
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int d = 0; d < D_HEAD; ++d) s = fmaf(qs[t][d], kr[d], s);
-        ps[t][tid] = masked ? -10000.0f : s;                   // submodules.py:261
+        for (int d = 0; d < D_HEAD; d += 4) {
+          const float4 qv = qs[t][d >> 2][kh];
+          s0 = fmaf(qv.x, kx[d], s0);
+          s1 = fmaf(qv.y, kx[d + 1], s1);
+          s2 = fmaf(qv.z, kx[d + 2], s2);
+          s3 = fmaf(qv.w, kx[d + 3], s3);
+        }
+        ps[kh][t][kj] = masked ? -10000.0f : (s0 + s1) + (s2 + s3);   // submodules.py:261
       }
     }
     __syncthreads();
-    if (tid < T) {
-      float mx = -INFINITY;
-      for (int j = 0; j < Tk; ++j) mx = fmaxf(mx, ps[tid][j]);
-      float sum = 0.f;
-      for (int j = 0; j < Tk; ++j) {
-        const float e = expf(ps[tid][j] - mx);
-        ps[tid][j] = e;
-        sum += e;
-      }
-      const float inv = 1.0f / sum;
-      for (int j = 0; j < Tk; ++j) {
-        const float p = (j < off) ? 0.f : ps[tid][j] * inv;    // submodules.py:262
-        ps[tid][j] = p;
-        Pg[tid * Tk + j] = p;
+    if (threadIdx.x == 0) PROF_MARK(3);
+    // masked softmax: 8 lanes per (head, query) row, NT / 8 rows in flight
+    {
+      const int g = tid >> 3, l8 = tid & 7;
+      for (int r = g; r < nq; r += NT / 8) {
+        const int h = r / T, t = r - h * T;
+        float* pr = &ps[h][t][0];
+        float e[6];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int j = l8 + 8 * k;
+          e[k] = j < Tk ? pr[j] : -INFINITY;
+          mx = fmaxf(mx, e[k]);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          e[k] = (l8 + 8 * k < Tk) ? expf(e[k] - mx) : 0.f;
+          sum += e[k];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        float* pg = Pg + (size_t)(h * T + t) * Tk;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int j = l8 + 8 * k;
+          if (j < Tk) {
+            const float p = (j < off) ? 0.f : e[k] * inv;          // submodules.py:262
+            pr[j] = p;
+            pg[j] = p;
+          }
+        }
       }
     }
   } else {
-    float tmp[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-      if (tid + i * 64 < T * Tk) tmp[i] = Pg[tid + i * 64];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int idx = tid + i * 64;
-      if (idx < T * Tk) ps[idx / Tk][idx % Tk] = tmp[i];
+    for (int i = tid; i < N_HEADS * T * Tk; i += NT) {
+      const int r = i / Tk, j = i - r * Tk, h = r / T, t = r - h * T;
+      ps[h][t][j] = Pg[i];
     }
   }
+  // first batch of this thread's V column travels while the barrier is reached
+  float vb[8];
+  if (tid < D_MODEL) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vb[k] = k < Tk ? vcol[(size_t)k * a.ldv] : 0.f;
+  }
   __syncthreads();
-  if (tid < D_HEAD) {
+  if (threadIdx.x == 0) PROF_MARK(4);
+  if (tid < D_MODEL) {
+    const int h = tid / D_HEAD;
     float acc[MAX_T];
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t) acc[t] = 0.f;
-    for (int j = 0; j < Tk; ++j) {
-      const float vj = vs[j][tid];
+    for (int j0 = 0; j0 < Tk; j0 += 8) {
+      float vn[8];
 #pragma unroll
-      for (int t = 0; t < MAX_T; ++t)
-        if (t < T) acc[t] = fmaf(ps[t][j], vj, acc[t]);
+      for (int k = 0; k < 8; ++k) vn[k] = (j0 + 8 + k < Tk) ? vcol[(size_t)(j0 + 8 + k) * a.ldv] : 0.f;   // next batch in flight
+      // V beyond Tk is zero, so stale P columns in [Tk, 48) do not matter (they are finite: the buffer is zeroed below)
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t) {
+        if (t < T) {
+          const float4 p0 = *reinterpret_cast<const float4*>(&ps[h][t][j0]);
+          const float4 p1 = *reinterpret_cast<const float4*>(&ps[h][t][j0 + 4]);
+          float s0 = fmaf(p0.x, vb[0], acc[t]), s1 = p0.y * vb[1];
+          s0 = fmaf(p0.z, vb[2], s0);
+          s1 = fmaf(p0.w, vb[3], s1);
+          s0 = fmaf(p1.x, vb[4], s0);
+          s1 = fmaf(p1.y, vb[5], s1);
+          s0 = fmaf(p1.z, vb[6], s0);
+          s1 = fmaf(p1.w, vb[7], s1);
+          acc[t] = s0 + s1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vb[k] = vn[k];
     }
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t)
-      if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + h * D_HEAD + tid] = __float2bfloat16(acc[t]);
+      if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + tid] = __float2bfloat16(acc[t]);
   }
   PROF_END();
 }
