@@ -1067,7 +1067,8 @@ struct PartIn {            // split-K output waiting to be folded into the resid
 static int run_norm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, float* r, const float* g1, const float* g2, bf16* n, int M,
                     const PartIn& p = PartIn(), bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
   NormArgs a{r, g1, g2, n, M, p.part, p.nsplit, p.stride, p.bias, p.scale, kv, ln.slots, rows_per_stream, kv_row_off};
-  KLAUNCH(launch_kernel(norm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
+  if (p.nsplit > 2) KLAUNCH(launch_kernel(norm_kernel<MAX_SPLITS>, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
+  else KLAUNCH(launch_kernel(norm_kernel<2>, dim3((M + 7) / 8), dim3(256), 0, st, e->pdl, a));
   return 0;
 }
 
@@ -1087,6 +1088,7 @@ static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M,
   int splits = 1;
   while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
   if (const char* v = getenv("TONE_SPLITK")) splits = atoi(v);
+  splits = std::max(1, std::min(splits, std::min(e->max_splits, (int)MAX_SPLITS)));
   GemmArgs b = dense_args(M, D_FF / splits, ln.h, ln.part, D_MODEL, nullptr, 1.f);
   b.lda = D_FF;
   b.z_stride = (long long)e->rows_alloc * D_MODEL;
@@ -1351,7 +1353,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     } else if (l == 14) {
       UpsampleArgs ua{ln.r_full, ln.r_red, ff.part, ff.nsplit, ff.stride, ff.bias, ff.scale,
                       L.n_out, e->L[15].n_ff1, ln.n, B, T, T2};
-      KLAUNCH(launch_kernel(upsample_norm_kernel, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
+      if (ff.nsplit > 2) KLAUNCH(launch_kernel(upsample_norm_kernel<MAX_SPLITS>, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
+      else KLAUNCH(launch_kernel(upsample_norm_kernel<2>, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, ln.r_full, B * T));
     } else if (l == 15) {
       RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
