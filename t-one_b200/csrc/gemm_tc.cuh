@@ -1,7 +1,8 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[128 x BN] (fp32, TMEM) = A[128 x K] * W[BN x K]^T, bf16 operands.
 //
-// One output tile per CTA, 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM owner and
-// tcgen05.mma issuer (one lane), warps 2..5 = epilogue (one TMEM lane quarter each).  Operand tiles are
+// One output tile per CTA, 320 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM owner and
+// tcgen05.mma issuer (one lane), warps 2..9 = epilogue: two warps per TMEM lane quarter, each taking half of the tile's
+// columns in the accumulator phase and half of the quarter's rows in the coalesced write-out.  Operand tiles are
 // K-major rows of 64 bf16 (128 B) in the 128-byte swizzle, staged through a STAGES-deep mbarrier ring.
 //
 // The A tile is either 128 consecutive rows of a dense [M][K] activation matrix, or a GATHER of G boxes of R
@@ -15,6 +16,9 @@
 #include "common.cuh"
 
 namespace tone {
+
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_THREADS = 256;
 
 enum GemmKind : int {
   G_STORE_F32 = 0,  // out fp32 = acc + bias                                 (q/k/v, out-linear, reduction pw)
@@ -120,7 +124,7 @@ __device__ __forceinline__ RowInfo row_info(const GemmArgs& a, int row_in_tile) 
 // Per-tile constants (bias, or folded BatchNorm scale/shift per output column) are staged in shared memory by the
 // epilogue warps while the main loop runs; they are weights, so this happens before the PDL wait.
 template <int KIND, int BN>
-__device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..127*/) {
+__device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..255*/) {
   const int n0 = blockIdx.y * BN;
   if constexpr (KIND == G_PARTIAL) {
     return;
@@ -136,7 +140,7 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
     if (t < BN) s_c0[t] = __ldg(a.bias + n0 + t);
     // depthwise taps [31][32] + bias [32] of this tile's 32 channels, behind the per-column constants
     float* wS = s_c1 + 128;
-    for (int i = t; i < 32 * 32; i += 128) {
+    for (int i = t; i < 32 * 32; i += EPI_THREADS) {
       const int j = i >> 5, c = i & 31;
       wS[i] = (j < 31) ? __ldg(a.dw_w + j * 384 + blockIdx.y * 32 + c) : __ldg(a.dw_b + blockIdx.y * 32 + c);
     }
@@ -153,6 +157,8 @@ struct OutCfg {
   static constexpr int STRIDE = ROW_BYTES + 16;   // +16 B: float4 stores of a quarter-warp hit distinct banks
   static constexpr int LPR = ROW_BYTES / 16;      // lanes per output row in the coalesced phase
   static constexpr int RPI = 32 / LPR;            // rows per warp instruction
+  static constexpr int NIT = 16 / RPI;            // write-out iterations per warp (16 rows each: two warps per quarter)
+  static_assert(RPI <= 16, "a write-out instruction must stay inside one warp's 16 rows");
 };
 
 template <int KIND>
@@ -167,19 +173,22 @@ __device__ __forceinline__ char* out_row_ptr(const GemmArgs& a, const RowInfo& r
     return reinterpret_cast<char*>(reinterpret_cast<bf16*>(a.out) + ri.out_row * (long long)a.ldo + n0_elems);
 }
 
-// Epilogue of one warp (TMEM lanes / tile rows 32q .. 32q+31), two phases:
-//  1. each thread owns one accumulator row: tcgen05.ld 16 columns at a time, apply the column-wise math (bias,
+// Epilogue of one warp.  Warps (q, hf), hf = 0 | 1, share TMEM lanes / tile rows 32q .. 32q+31.  Two phases:
+//  1. each thread owns one accumulator row and HALF of its columns (hf): tcgen05.ld, apply the column-wise math (bias,
 //     activation, gating, folded BatchNorm), and park the result in shared memory in its final element type;
-//  2. the warp writes its 32 rows back out with lanes running along the row, so every global store (and the
-//     residual read of G_RESID) is a contiguous 16 B-per-lane access.
+//  2. after the 8 epilogue warps have met, warp (q, hf) writes rows 32q + 16hf .. +15 back out with lanes running along
+//     the row, so every global store (and the residual read of G_RESID) is a contiguous 16 B-per-lane access.
 // The staging area is the operand ring, which is idle once the accumulator barrier has fired.
+__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int KIND, int BN>
-__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int q, int lane, char* stage,
+__device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_base, int q, int hf, int lane, char* stage,
                                          const float* s_c0, const float* s_c1, uint64_t* tmem_full) {
   using O = OutCfg<KIND, BN>;
   const int n0 = blockIdx.y * BN;
 
   if constexpr (KIND == G_DECODER) {
+    if (hf) return;
     const RowInfo ri = row_info<KIND>(a, q * 32 + lane);
     float lg[48];
     mbar_wait(tmem_full, 0);
@@ -210,35 +219,21 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       if (a.aux) *reinterpret_cast<float2*>(a.aux + ri.out_row * 2) = make_float2(lg[33] - lse, lg[34] - lse);
     }
     return;
-  } else {
-    // element offset of this tile's first output column
-    const int n0_out = (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) ? blockIdx.y * (BN / 2) : n0;
-    // phase-2 geometry (also used to prefetch the residual before the accumulator is ready)
-    const int sub_row = lane / O::LPR, cb = (lane % O::LPR) * 16;
-    float4 rres[32 / O::RPI];
-    if constexpr (KIND == G_RESID) {
-#pragma unroll
-      for (int it = 0; it < 32 / O::RPI; ++it) {
-        const RowInfo ri = row_info<KIND>(a, q * 32 + it * O::RPI + sub_row);
-        if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
-      }
-    }
-    // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
+  } else if constexpr (KIND == G_GLU_DW) {
+    // experimental fused conv module (off by default): one warp per quarter does all columns, then the depthwise stage
+    const int n0_out = blockIdx.y * (BN / 2);
     float rs = 1.f;
-    if constexpr (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) {
-      if (a.ss) {
-        const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
-        if (rme.valid) {
-          const float* sp = a.ss + rme.out_row * a.ss_ld;
-          float t = 0.f;
-          for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
-          rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);   // 384^-1/2, eps outside the sqrt (submodules.py:50-52)
-        }
+    if (a.ss) {
+      const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
+      if (rme.valid) {
+        const float* sp = a.ss + rme.out_row * a.ss_ld;
+        float t = 0.f;
+        for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
+        rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
       }
     }
-    // G_GLU_DW: the cached depthwise columns of this warp's (up to 3) streams are fetched while the main loop runs
-    float dwc[KIND == G_GLU_DW ? 3 : 1][KIND == G_GLU_DW ? 30 : 1];
-    if constexpr (KIND == G_GLU_DW) {
+    float dwc[3][30];
+    if (!hf) {
 #pragma unroll
       for (int si = 0; si < 3; ++si) {
         const int g = q + 4 * si, b = blockIdx.x * a.G + g;
@@ -250,20 +245,116 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       }
     }
     mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (!hf) {
+      float acc[BN];
+      tmem_load_row<BN>(tmem_row_base, acc);
+      const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
+      const uint32_t c0a = smem_u32(s_c0);
+      constexpr int HW = BN / 2;
+#pragma unroll
+      for (int c = 0; c < HW; c += 8) {
+        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
+        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fmaf(acc[c + i], rs, gb[i]) * sigmoid_f(fmaf(acc[HW + c + i], rs, ub[i]));
+        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                         pack_bf16x2(r[6], r[7])));
+      }
+    }
+    bar_epilogue();   // the whole GLU tile is staged
+    if (hf) return;
+    static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
+    const int T = a.R;
+    const int cg = blockIdx.y * 32 + lane;            // global channel
+    const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
+    const float bias = wS[31 * 32 + lane];
+#pragma unroll
+    for (int si = 0; si < 3; ++si) {
+      const int g = q + 4 * si, b = blockIdx.x * a.G + g;
+      if (g < a.G && b < a.M) {
+        bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
+        float col[30 + 13];
+#pragma unroll
+        for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
+#pragma unroll
+        for (int t = 0; t < 13; ++t)
+          if (t < T)
+            col[30 + t] = __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
+        float acc2[13];
+#pragma unroll
+        for (int t = 0; t < 13; ++t) acc2[t] = bias;
+#pragma unroll
+        for (int j = 0; j < 31; ++j) {
+          const float wj = wS[j * 32 + lane];
+#pragma unroll
+          for (int t = 0; t < 13; ++t)
+            if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
+        }
+        bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
+#pragma unroll
+        for (int t = 0; t < 13; ++t)
+          if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
+#pragma unroll
+        for (int i = 0; i < 30; ++i) {
+          float vsel = col[i];
+#pragma unroll
+          for (int t = 1; t <= 13; ++t)
+            if (t == T) vsel = col[i + t];
+          cache[i * 384] = __float2bfloat16(vsel);
+        }
+      }
+    }
+    (void)n0_out;
+    return;
+  } else {
+    constexpr bool gated = (KIND == G_SWIGLU || KIND == G_GLU);
+    // element offset of this tile's first output column
+    const int n0_out = gated ? blockIdx.y * (BN / 2) : n0;
+    // phase-2 geometry (also used to prefetch the residual before the accumulator is ready)
+    const int row0 = q * 32 + hf * 16;                       // first of this warp's 16 write-out rows
+    const int sub_row = lane / O::LPR, cb = (lane % O::LPR) * 16;
+    float4 rres[O::NIT];
+    if constexpr (KIND == G_RESID) {
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        const RowInfo ri = row_info<KIND>(a, row0 + it * O::RPI + sub_row);
+        if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
+      }
+    }
+    // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
+    float rs = 1.f;
+    if constexpr (gated) {
+      if (a.ss) {
+        const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
+        if (rme.valid) {
+          const float* sp = a.ss + rme.out_row * a.ss_ld;
+          float t = 0.f;
+          for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
+          rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);   // 384^-1/2, eps outside the sqrt (submodules.py:50-52)
+        }
+      }
+    }
+    mbar_wait(tmem_full, 0);
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
 
-    // ---- phase 1: accumulator row -> final-type row in shared memory (all TMEM loads in flight, one wait)
-    float acc[BN];
-    tmem_load_row<BN>(tmem_row_base, acc);
+    // ---- phase 1: half of the accumulator row -> final-type row in shared memory (all TMEM loads in flight, one wait)
     const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
     const uint32_t c0a = smem_u32(s_c0), c1a = smem_u32(s_c1);
     if constexpr (O::f32) {
+      constexpr int NC = BN / 2;                 // this warp's columns [hf * NC, hf * NC + NC)
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
 #pragma unroll
-      for (int c = 0; c < BN; c += 4) {
+      for (int c = 0; c < NC; c += 4) {
         float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
         if constexpr (KIND != G_PARTIAL) {
-          const float4 bb = lds128(c0a + c * 4);
+          const float4 bb = lds128(c0a + (cbase + c) * 4);
           o.x += bb.x;
           o.y += bb.y;
           o.z += bb.z;
@@ -275,93 +366,67 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
           o.z *= a.scale;
           o.w *= a.scale;
         }
-        sts128(srow + c * 4, o);
+        sts128(srow + (cbase + c) * 4, o);
       }
-    } else if constexpr (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) {
+    } else if constexpr (gated) {
       constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
+      constexpr int NC = HW / 2;  // this warp's output columns [hf * NC, hf * NC + NC)
+      const int cbase = hf * NC;
+      float ag[NC], av[NC];
+      {
+        uint32_t* rg = reinterpret_cast<uint32_t*>(ag);
+        uint32_t* rv = reinterpret_cast<uint32_t*>(av);
 #pragma unroll
-      for (int c = 0; c < HW; c += 8) {
-        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
-        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
+        for (int c = 0; c < NC; c += 16) {
+          tmem_ld16_async(tmem_row_base + cbase + c, rg + c);
+          tmem_ld16_async(tmem_row_base + HW + cbase + c, rv + c);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; c += 16) {
+          tmem_regs_ready16(rg + c);
+          tmem_regs_ready16(rv + c);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        const float4 g0 = lds128(c0a + (cbase + c) * 4), g1 = lds128(c0a + (cbase + c) * 4 + 16);
+        const float4 u0 = lds128(c0a + (HW + cbase + c) * 4), u1 = lds128(c0a + (HW + cbase + c) * 4 + 16);
         const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
         float r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float x = fmaf(acc[c + i], rs, gb[i]), y = fmaf(acc[HW + c + i], rs, ub[i]);
+          const float x = fmaf(ag[c + i], rs, gb[i]), y = fmaf(av[c + i], rs, ub[i]);
           r[i] = (KIND == G_SWIGLU) ? silu_f(x) * y : x * sigmoid_f(y);
         }
-        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                                         pack_bf16x2(r[6], r[7])));
+        sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                                   pack_bf16x2(r[6], r[7])));
       }
     } else {  // G_CONV0 / G_CONV1: folded BatchNorm + SiLU per output channel
+      constexpr int NC = BN / 2;
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
 #pragma unroll
-      for (int c = 0; c < BN; c += 8) {
-        const float4 a0 = lds128(c0a + c * 4), a1 = lds128(c0a + c * 4 + 16);
-        const float4 b0 = lds128(c1a + c * 4), b1 = lds128(c1a + c * 4 + 16);
+      for (int c = 0; c < NC; c += 8) {
+        const float4 a0 = lds128(c0a + (cbase + c) * 4), a1 = lds128(c0a + (cbase + c) * 4 + 16);
+        const float4 b0 = lds128(c1a + (cbase + c) * 4), b1 = lds128(c1a + (cbase + c) * 4 + 16);
         const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = silu_f(acc[c + i] * al[i] + be[i]);
-        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                                         pack_bf16x2(r[6], r[7])));
+        sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                                   pack_bf16x2(r[6], r[7])));
       }
     }
-    if constexpr (KIND == G_GLU_DW) {
-      // ---- depthwise stage: warp w takes streams w, w+4, ... of this tile, lane = channel.  Column = [30 cached
-      // rows | T new rows from the staged GLU tile]; e = silu(b' + sum_j w'[j] col[t+j]); cache' = last 30 rows.
-      static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the whole GLU tile is staged
-      const int T = a.R;
-      const int cg = blockIdx.y * 32 + lane;            // global channel
-      const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
-      const float bias = wS[31 * 32 + lane];
-#pragma unroll
-      for (int si = 0; si < 3; ++si) {
-        const int g = q + 4 * si, b = blockIdx.x * a.G + g;
-        if (g < a.G && b < a.M) {
-          bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
-          float col[30 + 13];
-#pragma unroll
-          for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
-#pragma unroll
-          for (int t = 0; t < 13; ++t)
-            if (t < T)
-              col[30 + t] =
-                  __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
-          float acc2[13];
-#pragma unroll
-          for (int t = 0; t < 13; ++t) acc2[t] = bias;
-#pragma unroll
-          for (int j = 0; j < 31; ++j) {
-            const float wj = wS[j * 32 + lane];
-#pragma unroll
-            for (int t = 0; t < 13; ++t)
-              if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
-          }
-          bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
-#pragma unroll
-          for (int t = 0; t < 13; ++t)
-            if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
-#pragma unroll
-          for (int i = 0; i < 30; ++i) {
-            float vsel = col[i];
-#pragma unroll
-            for (int t = 1; t <= 13; ++t)
-              if (t == T) vsel = col[i + t];
-            cache[i * 384] = __float2bfloat16(vsel);
-          }
-        }
-      }
-      return;
-    }
-    __syncwarp();
+    bar_epilogue();   // both halves of every row are staged
 
-    // ---- phase 2: coalesced write-out of this warp's 32 rows
+    // ---- phase 2: coalesced write-out of this warp's 16 rows
 #pragma unroll
-    for (int it = 0; it < 32 / O::RPI; ++it) {
-      const int row = q * 32 + it * O::RPI + sub_row;
+    for (int it = 0; it < O::NIT; ++it) {
+      const int row = row0 + it * O::RPI + sub_row;
       const RowInfo ri = row_info<KIND>(a, row);
       if constexpr (KIND == G_RESID) {
         float sq = 0.f;
@@ -387,9 +452,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         }
       } else if (ri.valid) {
         char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-        {
-          *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
-        }
+        *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
       }
     }
   }
@@ -397,7 +460,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <int KIND, int BN, bool DEEP>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmAw,
                                                       const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   using Cfg = TileCfg<BN, DEEP>;
@@ -525,12 +588,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       umma_commit(tmem_full);        // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
-    const int q = warp & 3;
+    // ---------------- epilogue: warps 2..9; warp w owns TMEM lanes 32*(w%4) .. +31, column half (w-2)/4
+    const int q = warp & 3, hf = (warp - 2) >> 2;
     stage_constants<KIND, BN>(a, s_c0, s_c1, threadIdx.x - 64);
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    bar_epilogue();                                  // the eight epilogue warps only
     pdl_wait();
-    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q, lane, reinterpret_cast<char*>(sA), s_c0,
+    epilogue<KIND, BN>(a, tmem_base + (static_cast<uint32_t>(q * 32) << 16), q, hf, lane, reinterpret_cast<char*>(sA), s_c0,
                        s_c1, tmem_full);
   }
   tc_fence_before();
@@ -574,9 +637,9 @@ inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const
                                   int num_sms, int splits = 1) {
   const dim3 grid(m_tiles, n_tiles, splits);
   if (m_tiles * n_tiles * splits <= 2 * num_sms)
-    return launch_kernel(gemm_tc_kernel<KIND, BN, true>, grid, dim3(192), TileCfg<BN, true>::SMEM_BYTES, st, pdl, tmA,
+    return launch_kernel(gemm_tc_kernel<KIND, BN, true>, grid, dim3(GEMM_THREADS), TileCfg<BN, true>::SMEM_BYTES, st, pdl, tmA,
                          tmAw, tmB, a);
-  return launch_kernel(gemm_tc_kernel<KIND, BN, false>, grid, dim3(192), TileCfg<BN, false>::SMEM_BYTES, st, pdl, tmA,
+  return launch_kernel(gemm_tc_kernel<KIND, BN, false>, grid, dim3(GEMM_THREADS), TileCfg<BN, false>::SMEM_BYTES, st, pdl, tmA,
                        tmAw, tmB, a);
 }
 
