@@ -623,77 +623,85 @@ struct DwArgs {
   int T;
 };
 
-// One CTA per stream, 192 threads.  The [30 cached | T new] x 384 tile is staged in shared memory with 16-byte
-// coalesced loads (all in flight at once); thread c then owns channels 2c, 2c+1: taps in registers, inputs streamed
-// from smem.  The new cache is rows [T, T+30) of the tile, copied back with coalesced 16-byte stores.
-constexpr int DW_THREADS = 192;
+// Two CTAs per stream (192 channels each), 384 threads = (channel, half of the output frames).  The
+// [30 cached | T new] x 192 tile is staged in shared memory with 16-byte coalesced loads (all in flight at once); each
+// thread then owns one channel and ceil(T/2) output frames: taps in registers, inputs streamed from smem.  The new
+// cache is rows [T, T+30) of the tile, copied back with coalesced 16-byte stores.
+constexpr int DW_CH = 192;                       // channels per CTA
+constexpr int DW_THREADS = 2 * DW_CH;
 constexpr int DW_ROWS = CONV_S + MAX_T;          // 43
-constexpr int DW_RV = D_MODEL / 8;               // uint4 per row
+constexpr int DW_RV = DW_CH / 8;                 // uint4 per tile row
+constexpr int DW_TH = (MAX_T + 1) / 2;           // output frames per thread (7)
 
 __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
-  __shared__ __align__(16) bf16 tile[DW_ROWS][D_MODEL];
+  __shared__ __align__(16) bf16 tile[DW_ROWS][DW_CH];
   PROF_DECL();
   PROF_BEGIN(5);
   pdl_launch_dependents();
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, c0 = blockIdx.y * DW_CH, tid = threadIdx.x;
   const int T = a.T;
-  // BN-folded taps of this thread's two channels: weights, fetched before the PDL wait
-  float2 w[CONV_S + 1];
+  const int cl = tid % DW_CH, th = tid / DW_CH;  // local channel, frame half
+  const int c = c0 + cl;
+  // BN-folded taps of this thread's channel: weights, fetched before the PDL wait
+  float w[CONV_S + 1];
 #pragma unroll
-  for (int j = 0; j <= CONV_S; ++j) w[j] = __ldg(reinterpret_cast<const float2*>(a.w + j * D_MODEL + 2 * tid));
-  const float2 bb = __ldg(reinterpret_cast<const float2*>(a.bias + 2 * tid));
+  for (int j = 0; j <= CONV_S; ++j) w[j] = __ldg(a.w + j * D_MODEL + c);
+  const float bb = __ldg(a.bias + c);
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
-  bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride;
+  bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride + c0;
   {
-    const uint4* c4 = reinterpret_cast<const uint4*>(cache);
-    const uint4* g4 = reinterpret_cast<const uint4*>(a.g + (size_t)b * T * D_MODEL);
+    const bf16* g = a.g + (size_t)b * T * D_MODEL + c0;
     uint4* t4 = reinterpret_cast<uint4*>(&tile[0][0]);
-    const int n_cache = CONV_S * DW_RV, n_all = (CONV_S + T) * DW_RV;
-    uint4 tmp[11];
+    const int n_cache = CONV_S * DW_RV, n_all = (CONV_S + T) * DW_RV;       // 720, <= 1032
+    uint4 tmp[3];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < 3; ++k) {
       const int i = tid + k * DW_THREADS;
-      if (i < n_all) tmp[k] = (i < n_cache) ? c4[i] : g4[i - n_cache];
+      if (i < n_all) {
+        const int r = i / DW_RV, v = i - r * DW_RV;
+        tmp[k] = (i < n_cache) ? *reinterpret_cast<const uint4*>(cache + (size_t)r * D_MODEL + v * 8)
+                               : *reinterpret_cast<const uint4*>(g + (size_t)(r - CONV_S) * D_MODEL + v * 8);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < 3; ++k) {
       const int i = tid + k * DW_THREADS;
       if (i < n_all) t4[i] = tmp[k];
     }
   }
   __syncthreads();
-  // y[t] = b' + sum_j w'[j] x[t + j]  (submodules.py:364-402 with BatchNorm folded), input-stationary order
-  float2 acc[MAX_T];
+  // y[t] = b' + sum_j w'[j] x[t + j]  (submodules.py:364-402 with BatchNorm folded), input-stationary order;
+  // this thread's frames: t0 .. t0 + DW_TH - 1 (clipped to T)
+  const int half = (T + 1) / 2;
+  const int t0 = th * half;
+  float acc[DW_TH];
 #pragma unroll
-  for (int t = 0; t < MAX_T; ++t) acc[t] = bb;
+  for (int t = 0; t < DW_TH; ++t) acc[t] = bb;
 #pragma unroll
-  for (int i = 0; i < DW_ROWS; ++i) {
-    if (i < CONV_S + T) {
-      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tile[i][2 * tid]));
+  for (int i = 0; i < CONV_S + DW_TH; ++i) {             // rows t0 + i of the tile
+    if (t0 + i < CONV_S + T) {
+      const float x = __bfloat162float(tile[t0 + i][cl]);
 #pragma unroll
-      for (int t = 0; t < MAX_T; ++t) {
-        const int j = i - t;                     // compile-time after unrolling
-        if (j >= 0 && j <= CONV_S && t < T) {
-          acc[t].x = fmaf(w[j].x, x.x, acc[t].x);
-          acc[t].y = fmaf(w[j].y, x.y, acc[t].y);
-        }
+      for (int t = 0; t < DW_TH; ++t) {
+        const int j = i - t;                               // compile-time after unrolling
+        if (j >= 0 && j <= CONV_S) acc[t] = fmaf(w[j], x, acc[t]);
       }
     }
   }
 #pragma unroll
-  for (int t = 0; t < MAX_T; ++t)
-    if (t < T)
-      *reinterpret_cast<__nv_bfloat162*>(a.e + (size_t)(b * T + t) * D_MODEL + 2 * tid) =
-          __floats2bfloat162_rn(silu_f(acc[t].x), silu_f(acc[t].y));
+  for (int t = 0; t < DW_TH; ++t)
+    if (t < half && t0 + t < T) a.e[(size_t)(b * T + t0 + t) * D_MODEL + c] = __float2bfloat16(silu_f(acc[t]));
   // new cache = last 30 rows of [cache | g]
   {
-    uint4* c4 = reinterpret_cast<uint4*>(cache);
     const uint4* t4 = reinterpret_cast<const uint4*>(&tile[T][0]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 2; ++k) {
       const int i = tid + k * DW_THREADS;
-      if (i < CONV_S * DW_RV) c4[i] = t4[i];
+      if (i < CONV_S * DW_RV) {
+        const int r = i / DW_RV, v = i - r * DW_RV;
+        *reinterpret_cast<uint4*>(cache + (size_t)r * D_MODEL + v * 8) = t4[i];
+      }
     }
   }
   PROF_END();
