@@ -262,12 +262,33 @@ __device__ __forceinline__ void scale_384(float4 (&x)[3], const float* g, float 
   }
 }
 
+// gains / bias of this lane's 12 columns, loaded BEFORE the programmatic-dependency wait (they are weights)
+struct Vec384 {
+  float4 v[3];
+};
+__device__ __forceinline__ Vec384 load_vec384(const float* g, int lane, float fill) {
+  Vec384 o;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    o.v[i] = g ? __ldg(reinterpret_cast<const float4*>(g + i * 128 + lane * 4)) : make_float4(fill, fill, fill, fill);
+  return o;
+}
+__device__ __forceinline__ void scale_384(float4 (&x)[3], const Vec384& g, float inv) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    x[i].x = g.v[i].x * (x[i].x * inv);
+    x[i].y = g.v[i].y * (x[i].y * inv);
+    x[i].z = g.v[i].z * (x[i].z * inv);
+    x[i].w = g.v[i].w * (x[i].w * inv);
+  }
+}
+
 // x += scale * (sum_z part[z] + bias): fixed summation order, so split-K stays deterministic.  All partial loads are
 // issued before the first add (a runtime-trip-count loop would serialise nsplit L2 round trips: 3.9 us -> 1.x us).
 constexpr int MAX_SPLITS = 8;
 template <int MAXS>
 __device__ __forceinline__ void add_partials_384(float4 (&x)[3], const float* part_row, int nsplit, long long stride,
-                                                 const float* bias, float scale, int lane) {
+                                                 const Vec384& bias, float scale, int lane) {
   float4 p[MAXS][3];
 #pragma unroll
   for (int z = 0; z < MAXS; ++z) {
@@ -278,7 +299,7 @@ __device__ __forceinline__ void add_partials_384(float4 (&x)[3], const float* pa
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    float4 s = *reinterpret_cast<const float4*>(bias + i * 128 + lane * 4);
+    float4 s = bias.v[i];
 #pragma unroll
     for (int z = 0; z < MAXS; ++z) {
       if (z < nsplit) {
@@ -301,22 +322,24 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
   PROF_DECL();
   PROF_BEGIN(2);
   pdl_launch_dependents();
-  pdl_wait();
-  if (threadIdx.x == 0) PROF_MARK(2);
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const Vec384 g1 = load_vec384(a.g1, lane, 1.f), g2 = load_vec384(a.g2, lane, 1.f);
+  const Vec384 bias = load_vec384(a.part ? a.bias : nullptr, lane, 0.f);
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   if (row >= a.M) return;
   float* rr = a.r + (size_t)row * D_MODEL;
   float4 x[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rr + i * 128 + lane * 4);
-  if (a.part) add_partials_384<MAXS>(x, a.part + (size_t)row * D_MODEL, a.nsplit, a.part_stride, a.bias, a.scale, lane);
-  if (a.g1) scale_384(x, a.g1, rms_inv_384(x), lane);
+  if (a.part) add_partials_384<MAXS>(x, a.part + (size_t)row * D_MODEL, a.nsplit, a.part_stride, bias, a.scale, lane);
+  if (a.g1) scale_384(x, g1, rms_inv_384(x));
   if (a.part || a.g1) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = x[i];
   }
-  if (a.g2) scale_384(x, a.g2, rms_inv_384(x), lane);
+  if (a.g2) scale_384(x, g2, rms_inv_384(x));
   if (a.n) {
     bf16* nr = a.n + (size_t)row * D_MODEL;
     bf16* kr = nullptr;
@@ -355,10 +378,12 @@ __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a
   PROF_DECL();
   PROF_BEGIN(3);
   pdl_launch_dependents();
-  pdl_wait();
-  if (threadIdx.x == 0) PROF_MARK(2);
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const Vec384 g_out = load_vec384(a.g_out, lane, 1.f), g_next = load_vec384(a.g_next, lane, 1.f);
+  const Vec384 bias = load_vec384(a.part ? a.bias : nullptr, lane, 0.f);
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
   if (row >= a.B * a.T) return;
   const int b = row / a.T, t = row - b * a.T;
   float* rr = a.r_full + (size_t)row * D_MODEL;
@@ -370,9 +395,9 @@ __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = *reinterpret_cast<const float4*>(rs + i * 128 + lane * 4);
     if (a.part)
-      add_partials_384<MAXS>(x, a.part + ((size_t)b * a.T2 + (t >> 1)) * D_MODEL, a.nsplit, a.part_stride, a.bias,
+      add_partials_384<MAXS>(x, a.part + ((size_t)b * a.T2 + (t >> 1)) * D_MODEL, a.nsplit, a.part_stride, bias,
                              a.scale, lane);
-    scale_384(x, a.g_out, rms_inv_384(x), lane);
+    scale_384(x, g_out, rms_inv_384(x));
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       y[i].x += x[i].x;
@@ -383,7 +408,7 @@ __global__ void __launch_bounds__(256) upsample_norm_kernel(const UpsampleArgs a
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = y[i];
-  scale_384(y, a.g_next, rms_inv_384(y), lane);
+  scale_384(y, g_next, rms_inv_384(y));
   bf16* nr = a.n + (size_t)row * D_MODEL;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
