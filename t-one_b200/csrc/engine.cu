@@ -144,7 +144,8 @@ struct tone_engine {
   // The batch is cut into up to n_lanes independent sub-batches whose kernel chains run concurrently (fork/join in
   // the captured graph): at small batch the step is bound by kernel-to-kernel latency, not by the SMs.
   struct Lane {
-    float *r_full, *r_red, *qkv, *P, *part;
+    float *r_full, *r_red, *qkv, *P;
+    __half* part;                       // split-K partial sums of the feed-forward down projection (fp16)
     bf16 *n, *h, *ctx, *g, *ebuf, *c1, *m_red, *rb;
     float* ss;                          // [rows][12] per-N-tile sums of squares of the residual rows (row-scale RMSNorm)
     CUtensorMap m_n, m_h, m_ctx, m_e, m_c1, m_mred, m_rb;
@@ -1057,7 +1058,7 @@ static GemmArgs dense_args(int M, int K, const bf16* A, void* out, int ldo, cons
   } while (0)
 
 struct PartIn {            // split-K output waiting to be folded into the residual stream by the next norm kernel
-  const float* part = nullptr;
+  const __half* part = nullptr;
   int nsplit = 0;
   long long stride = 0;
   const float* bias = nullptr;

@@ -64,7 +64,8 @@ __global__ void gemm_ref_kernel(const GemmArgs a, int n_out) {
     const bf16* w = a.W + (long long)col * a.ldw + (long long)z * klen;
     float acc = 0.f;
     for (int k = 0; k < klen; ++k) acc += __bfloat162float(ar[k]) * __bfloat162float(w[k]);
-    reinterpret_cast<float*>(a.out)[z * a.z_stride + (long long)row * a.ldo + col] = acc;
+    reinterpret_cast<__half*>(a.out)[z * a.z_stride + (long long)row * a.ldo + col] =
+        __float2half_rn(fminf(fmaxf(acc, -65504.f), 65504.f));
   } else if constexpr (KIND == G_STORE_F32 || KIND == G_KV) {
     float v = ref_dot<KIND>(a, b, j, 0, col) + (a.bias ? a.bias[col] : 0.f);
     reinterpret_cast<float*>(a.out)[(long long)row * a.ldo + col] = v;

@@ -29,7 +29,8 @@ enum GemmKind : int {
   G_CONV1 = 5,      // c1 bf16 = silu(acc*alpha + beta)                      (gather A from x1 windows)
   G_KV = 6,         // out fp32 = acc + bias, gather A from [cache|new] rows (layers 14, 15)
   G_DECODER = 7,    // logprobs = log_softmax(acc + bias)[0:35], argmax      (BN = 48)
-  G_PARTIAL = 8,    // part[z] fp32 = acc over K slice z (split-K; blockIdx.z)  (ff down; summed by addnorm_kernel)
+  G_PARTIAL = 8,    // part[z] fp16 (saturating) = acc over K slice z (split-K; blockIdx.z)  (ff down; the norm kernel sums
+                    // the slices in fp32 in a fixed order)
   G_GLU_DW = 9,     // conv module in one kernel: GLU epilogue, then the causal depthwise conv k=31 + BN + SiLU over
                     // [30-row cache | T new rows] per stream and channel, cache roll included (tiles hold whole streams)
 };
@@ -152,7 +153,7 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
 // Output geometry of one tile row, in bytes of the FINAL output type.
 template <int KIND, int BN>
 struct OutCfg {
-  static constexpr bool f32 = (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_PARTIAL || KIND == G_RESID);
+  static constexpr bool f32 = (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_RESID);
   static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) ? BN : BN * 2);
   static constexpr int STRIDE = ROW_BYTES + 16;   // +16 B: float4 stores of a quarter-warp hit distinct banks
   static constexpr int LPR = ROW_BYTES / 16;      // lanes per output row in the coalesced phase
@@ -164,7 +165,7 @@ struct OutCfg {
 template <int KIND>
 __device__ __forceinline__ char* out_row_ptr(const GemmArgs& a, const RowInfo& ri, int n0_elems) {
   if constexpr (KIND == G_PARTIAL)
-    return reinterpret_cast<char*>(reinterpret_cast<float*>(a.out) + blockIdx.z * a.z_stride + ri.out_row * a.ldo + n0_elems);
+    return reinterpret_cast<char*>(reinterpret_cast<__half*>(a.out) + blockIdx.z * a.z_stride + ri.out_row * a.ldo + n0_elems);
   else if constexpr (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_RESID)
     return reinterpret_cast<char*>(reinterpret_cast<float*>(a.out) + ri.out_row * a.ldo + n0_elems);
   else if constexpr (KIND == G_CONV0)
@@ -353,7 +354,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 #pragma unroll
       for (int c = 0; c < NC; c += 4) {
         float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-        if constexpr (KIND != G_PARTIAL) {
+        {
           const float4 bb = lds128(c0a + (cbase + c) * 4);
           o.x += bb.x;
           o.y += bb.y;
@@ -402,6 +403,22 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         }
         sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
                                                    pack_bf16x2(r[6], r[7])));
+      }
+    } else if constexpr (KIND == G_PARTIAL) {   // raw K-slice sums as saturating fp16
+      constexpr int NC = BN / 2;
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __half2 hv = __floats2half2_rn(fminf(fmaxf(acc[c + 2 * i], -65504.f), 65504.f),
+                                               fminf(fmaxf(acc[c + 2 * i + 1], -65504.f), 65504.f));
+          pk[i] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        sts128u(srow + (cbase + c) * 2, make_uint4(pk[0], pk[1], pk[2], pk[3]));
       }
     } else {  // G_CONV0 / G_CONV1: folded BatchNorm + SiLU per output channel
       constexpr int NC = BN / 2;

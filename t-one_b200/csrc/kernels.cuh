@@ -232,7 +232,7 @@ struct NormArgs {
   bf16* n;
   int M;
   // optional split-K input: x = r + scale * (sum_z part[z][row] + bias) is formed (and written back to r) first
-  const float* part;
+  const __half* part;
   int nsplit;
   long long part_stride;
   const float* bias;
@@ -287,14 +287,14 @@ __device__ __forceinline__ void scale_384(float4 (&x)[3], const Vec384& g, float
 // issued before the first add (a runtime-trip-count loop would serialise nsplit L2 round trips: 3.9 us -> 1.x us).
 constexpr int MAX_SPLITS = 8;
 template <int MAXS>
-__device__ __forceinline__ void add_partials_384(float4 (&x)[3], const float* part_row, int nsplit, long long stride,
+__device__ __forceinline__ void add_partials_384(float4 (&x)[3], const __half* part_row, int nsplit, long long stride,
                                                  const Vec384& bias, float scale, int lane) {
-  float4 p[MAXS][3];
+  uint2 p[MAXS][3];     // 4 halfs each
 #pragma unroll
   for (int z = 0; z < MAXS; ++z) {
     if (z < nsplit) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) p[z][i] = *reinterpret_cast<const float4*>(part_row + z * stride + i * 128 + lane * 4);
+      for (int i = 0; i < 3; ++i) p[z][i] = *reinterpret_cast<const uint2*>(part_row + z * stride + i * 128 + lane * 4);
     }
   }
 #pragma unroll
@@ -303,10 +303,12 @@ __device__ __forceinline__ void add_partials_384(float4 (&x)[3], const float* pa
 #pragma unroll
     for (int z = 0; z < MAXS; ++z) {
       if (z < nsplit) {
-        s.x += p[z][i].x;
-        s.y += p[z][i].y;
-        s.z += p[z][i].z;
-        s.w += p[z][i].w;
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&p[z][i].x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&p[z][i].y));
+        s.x += lo.x;
+        s.y += lo.y;
+        s.z += hi.x;
+        s.w += hi.y;
       }
     }
     x[i].x += scale * s.x;
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
 struct UpsampleArgs {
   float* r_full;
   const float* r_red;
-  const float* part;      // split-K output of layer 14's second feed-forward (added to r_red rows first)
+  const __half* part;     // split-K output of layer 14's second feed-forward (added to r_red rows first)
   int nsplit;
   long long part_stride;
   const float* bias;
