@@ -1299,7 +1299,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.k_ln_b = L.kln_b;
       at.mask_mode = (l == 14) ? 2 : 1;
     }
-    if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B), dim3(ATT_THREADS_REC), 0, st, e->pdl, at));
+    if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), 0, st, e->pdl, at));
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
     RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));

@@ -478,24 +478,27 @@ __device__ __forceinline__ void ln_rope_row(const float* src, const float* w, co
   for (int i = 0; i < D_HEAD; ++i) dst[i] = x[i] * scale;
 }
 
-// One CTA per STREAM, all 8 heads.
-//   RECOMPUTE (layers 0, 7, 14, 15; 512 threads): thread = (key row j, head) or (query row t, head): per-head LayerNorm
+// Score-sharing layers: one CTA per STREAM, all 8 heads.  Recompute layers: two CTAs per stream, 4 heads each.
+//   RECOMPUTE (layers 0, 7, 14, 15; 256 threads): thread = (key row j, head) or (query row t, head): per-head LayerNorm
 //   + RoPE with the row in registers; query rows go to shared memory, key rows stay in registers and produce their
 //   column of the score matrix; one warp per (head, query) row does the masked softmax and publishes P for the
 //   score-sharing layers.
 //   all layers (384 threads in the score-sharing instantiation): thread = (head, dim) accumulates ctx[t] over the keys,
 //   reading V coalesced straight from global memory in batches of 8 keys (each V element is used by exactly one
 //   thread), P broadcast from shared memory.
-constexpr int ATT_THREADS_REC = 512;
+constexpr int ATT_THREADS_REC = 256;
+constexpr int ATT_HEADS_REC = 4;            // heads per CTA in the recompute instantiation (grid.y = 2)
 constexpr int ATT_THREADS = D_MODEL;       // 384
 constexpr int ATT_TK = MHSA_S + MAX_T;     // 43
 
 template <bool RECOMPUTE>
 __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) attention_kernel(const AttnArgs a) {
   constexpr int NT = RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS;
-  // query rows as [t][d / 4][head] float4: the 8 heads of a quarter-warp read 8 consecutive 16 B words (no conflicts)
-  __shared__ float4 qs[RECOMPUTE ? MAX_T : 1][D_HEAD / 4][N_HEADS];             // 20 KB (recompute only)
-  __shared__ __align__(16) float ps[N_HEADS][MAX_T][48];                        // 20 KB; columns >= Tk are zero in the P.V loop
+  constexpr int NH = RECOMPUTE ? ATT_HEADS_REC : N_HEADS;                       // heads handled by this CTA
+  constexpr int NC = NH * D_HEAD;                                               // channels handled by this CTA
+  // query rows as [t][d / 4][head] float4: the heads of a quarter-warp read consecutive 16 B words (no conflicts)
+  __shared__ float4 qs[RECOMPUTE ? MAX_T : 1][D_HEAD / 4][NH];                  // 10 KB (recompute only)
+  __shared__ __align__(16) float ps[NH][MAX_T][48];                             // columns >= Tk are zero in the P.V loop
   PROF_DECL();
   PROF_BEGIN(4);
   pdl_launch_dependents();
@@ -504,27 +507,28 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int T = a.T, Tk = a.Tk, S = a.S;
-  float* Pg = a.P + (size_t)b * N_HEADS * T * Tk;
-  const float* vcol = a.v + (size_t)b * Tk * a.ldv + tid;
+  const int h0 = RECOMPUTE ? blockIdx.y * NH : 0;        // first head of this CTA
+  float* Pg = a.P + ((size_t)b * N_HEADS + h0) * T * Tk;
+  const float* vcol = a.v + (size_t)b * Tk * a.ldv + h0 * D_HEAD + tid;
   // padding columns [Tk, Tk + 8) are read by the 8-wide P.V loop: keep them zero (all other phases touch j < Tk only)
-  for (int i = tid; i < N_HEADS * MAX_T * 8; i += NT) {
+  for (int i = tid; i < NH * MAX_T * 8; i += NT) {
     const int j = Tk + (i & 7);
     if (j < 48) (&ps[0][0][0])[(i >> 3) * 48 + j] = 0.f;
   }
 
   if constexpr (RECOMPUTE) {
-    const int nk = Tk * N_HEADS, nq = T * N_HEADS;      // <= 344 + 104 <= 512
+    const int nk = Tk * NH, nq = T * NH;                // <= 172 + 52 <= 256
     float kx[D_HEAD];
     int kj = -1, kh = 0;
     if (tid < nk) {
-      kj = tid / N_HEADS;
-      kh = tid - kj * N_HEADS;
-      ln_rope_row(a.k + (size_t)(b * Tk + kj) * a.ldk + kh * D_HEAD, a.k_ln_w, a.k_ln_b,
+      kj = tid / NH;
+      kh = tid - kj * NH;
+      ln_rope_row(a.k + (size_t)(b * Tk + kj) * a.ldk + (h0 + kh) * D_HEAD, a.k_ln_w, a.k_ln_b,
                   a.rope_cos + (kj - S + MHSA_S) * 16, a.rope_sin + (kj - S + MHSA_S) * 16, 1.0f, kx);
     } else if (tid < nk + nq) {
-      const int i = tid - nk, t = i / N_HEADS, h = i - t * N_HEADS;
+      const int i = tid - nk, t = i / NH, h = i - t * NH;
       float qx[D_HEAD];
-      ln_rope_row(a.q + (size_t)(b * T + t) * a.ldq + h * D_HEAD, a.q_ln_w, a.q_ln_b,
+      ln_rope_row(a.q + (size_t)(b * T + t) * a.ldq + (h0 + h) * D_HEAD, a.q_ln_w, a.q_ln_b,
                   a.rope_cos + (t + MHSA_S) * 16, a.rope_sin + (t + MHSA_S) * 16,
                   0.14433756729740643f /* 1/sqrt(48) */, qx);
 #pragma unroll
@@ -590,20 +594,20 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
       }
     }
   } else {
-    for (int i = tid; i < N_HEADS * T * Tk; i += NT) {
+    for (int i = tid; i < NH * T * Tk; i += NT) {
       const int r = i / Tk, j = i - r * Tk, h = r / T, t = r - h * T;
       ps[h][t][j] = Pg[i];
     }
   }
   // first batch of this thread's V column travels while the barrier is reached
   float vb[8];
-  if (tid < D_MODEL) {
+  if (tid < NC) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) vb[k] = k < Tk ? vcol[(size_t)k * a.ldv] : 0.f;
   }
   __syncthreads();
   if (threadIdx.x == 0) PROF_MARK(4);
-  if (tid < D_MODEL) {
+  if (tid < NC) {
     const int h = tid / D_HEAD;
     float acc[MAX_T];
 #pragma unroll
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
     }
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t)
-      if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + tid] = __float2bfloat16(acc[t]);
+      if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + h0 * D_HEAD + tid] = __float2bfloat16(acc[t]);
   }
   PROF_END();
 }
