@@ -27,7 +27,7 @@ def main(path, out, title):
         n += 1
     with open(out, "w") as f:
         f.write(f"# {title}\n\n")
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` launch list of one step "
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` launch list "
                 "(cold-cache, serialised: compare SHARES, not absolutes).\n\n")
         f.write(f"launches: {n}, sum of durations: {total:.1f} us\n\n")
         f.write("| kernel | grid | launches | sum us | avg us | share |\n|---|---|---|---|---|---|\n")
