@@ -89,6 +89,14 @@ int tone_reset_slots(tone_engine* e, int32_t n, const int32_t* slots);
 int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm,
               float* logprobs, int32_t* tokens);
 
+/* Feature-input form of the step: replaces the exported graph built with `--skip-preprocessor`
+ * (tone/nn/model.py:151-160, tone/scripts/export.py:48-49), i.e. the acoustic model behind an external log-mel front
+ * end such as the Triton/DALI ensemble (triton/preprocessing/1/features_8k_tone.py).
+ *   feats  host fp16 [B][64][chunk_samples / 80]  log-mel features, (B, C = n_mels, T) like the reference
+ * The waveform state of the slots is left untouched; everything else is tone_step. */
+int tone_step_features(tone_engine* e, int32_t B, const int32_t* slots, const uint16_t* feats_fp16,
+                       float* logprobs, int32_t* tokens);
+
 /* Same step with inputs/outputs left in HBM: stage once, then step any number of times on
  * the staged chunk (benchmark "inputs already resident" leg).  tone_fetch copies the last
  * outputs to the host. */

@@ -136,6 +136,8 @@ struct tone_engine {
   // step inputs / outputs (batch order)
   int rows_alloc;
   int *d_slots, *d_pcm, *d_len_in, *d_tokens;
+  __half* d_feats;   // [max_batch][64][MAX_FRAMES] feature-input mode staging
+  uint16_t* p_feats; // pinned
   float* logprobs;
   float* d_aux;      // [rows][2] logprob of space / blank per frame (greedy fast path)
   int max_splits = 8;
@@ -154,6 +156,7 @@ struct tone_engine {
     // view of the sub-batch this lane is working on (set per step)
     const int* slots;
     const int* pcm;
+    const __half* feats;                 // non-null: feature-input mode
     int* len_in;
     float* lp_out;
     int* tok_out;
@@ -337,6 +340,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   rc |= dev_alloc(e, &e->d_slots, Bm);
   rc |= dev_alloc(e, &e->d_pcm, Bm * e->C);
   rc |= dev_alloc(e, &e->d_len_in, Bm);
+  rc |= dev_alloc(e, &e->d_feats, Bm * N_MELS * MAX_FRAMES);
   rc |= dev_alloc(e, &e->d_tokens, R);
   rc |= dev_alloc(e, &e->d_aux, R * 2);
   rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
@@ -372,6 +376,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK(cudaMallocHost((void**)&e->p_tokens, Bm * MAX_T * 4));
   CK(cudaMallocHost((void**)&e->p_logprobs, Bm * MAX_T * N_CLASSES * 4));
   CK(cudaMallocHost((void**)&e->p_aux, Bm * MAX_T * 2 * 4));
+  CK(cudaMallocHost((void**)&e->p_feats, Bm * N_MELS * MAX_FRAMES * 2));
 
   // activation-side tensor maps
   {
@@ -443,6 +448,7 @@ extern "C" void tone_destroy(tone_engine* e) {
   cudaFreeHost(e->p_tokens);
   cudaFreeHost(e->p_logprobs);
   cudaFreeHost(e->p_aux);
+  cudaFreeHost(e->p_feats);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1142,6 +1148,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     memset(&a, 0, sizeof(a));
     a.slots = ln.slots;
     a.pcm = ln.pcm;
+    a.feats_in = ln.feats;
     a.pre = e->st_pre;
     a.feat = e->st_feat;
     a.x1 = e->st_x1;
@@ -1384,7 +1391,7 @@ static int check_step_args(tone_engine* e, int B) {
 
 // Cut the batch into lanes and enqueue their kernel chains: lane 0 on `st`, the others on their own streams between
 // a fork event and per-lane join events (works both eagerly and under stream capture).
-static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
+static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps, bool features = false) {
   int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
   if (const char* v = getenv("TONE_FORCE_LANES")) nl = std::max(1, std::min(e->n_lanes, atoi(v)));
   nl = std::min(nl, B);
@@ -1397,6 +1404,7 @@ static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
     if (nb <= 0) continue;
     ln.slots = e->d_slots + b0;
     ln.pcm = e->d_pcm + (size_t)b0 * e->C;
+    ln.feats = features ? e->d_feats + (size_t)b0 * N_MELS * e->F : nullptr;
     ln.len_in = e->d_len_in + b0;
     ln.lp_out = e->logprobs + (size_t)b0 * e->T * N_CLASSES;
     ln.tok_out = e->d_tokens + (size_t)b0 * e->T;
@@ -1413,20 +1421,21 @@ static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps) {
   return 0;
 }
 
-static int launch_step(tone_engine* e, int B, cudaStream_t st) {
-  if (!e->cfg.use_graph) return enqueue_step(e, B, st, nullptr);
-  auto it = e->graphs.find(B);
+static int launch_step(tone_engine* e, int B, cudaStream_t st, bool features = false) {
+  if (!e->cfg.use_graph) return enqueue_step(e, B, st, nullptr, features);
+  const int key = B + (features ? (1 << 24) : 0);
+  auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     cudaGraph_t graph;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(e, B, e->stream, nullptr);
+    int rc = enqueue_step(e, B, e->stream, nullptr, features);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(TONE_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
     cudaGraphExec_t exec;
     CK(cudaGraphInstantiate(&exec, graph, 0));
     CK(cudaGraphDestroy(graph));
-    it = e->graphs.emplace(B, exec).first;
+    it = e->graphs.emplace(key, exec).first;
   }
   CK(cudaGraphLaunch(it->second, st));
   return 0;
@@ -1506,6 +1515,25 @@ extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const 
                          int32_t* tokens) {
   RC(tone_stage(e, B, slots, pcm));
   RC(launch_step(e, B, e->stream));
+  return tone_fetch(e, B, logprobs, tokens);
+}
+
+// Feature-input mode (reference skip_preprocessor=True, tone/nn/model.py:151-160; the Triton ensemble feeds DALI log-mel
+// features, triton/preprocessing/1/features_8k_tone.py): feats = host fp16 [B][64][F], F = chunk_samples / 80.
+extern "C" int tone_step_features(tone_engine* e, int32_t B, const int32_t* slots, const uint16_t* feats,
+                                  float* logprobs, int32_t* tokens) {
+  RC(check_step_args(e, B));
+  if (!slots || !feats) return fail(TONE_EINVAL, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < B; ++i)
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
+      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
+  const size_t nf = (size_t)B * N_MELS * e->F;
+  memcpy(e->p_slots, slots, (size_t)B * 4);
+  memcpy(e->p_feats, feats, nf * 2);
+  CK(cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_feats, e->p_feats, nf * 2, cudaMemcpyHostToDevice, e->stream));
+  RC(launch_step(e, B, e->stream, true));
   return tone_fetch(e, B, logprobs, tokens);
 }
 

@@ -33,6 +33,8 @@ constexpr int MAX_T = 13;
 struct BeginArgs {
   const int* slots;          // [B]
   const int* pcm;            // [B][C] int32
+  const __half* feats_in;    // nullable: feature-input mode (reference skip_preprocessor=True, tone/nn/model.py:151-160):
+                             // [B][64][F] fp16 log-mel features replace the waveform front end; `pre` is left untouched
   __half* pre;               // [slots][80] last samples of the previous chunk (fp16-exact values)
   bf16* feat;                // [slots][FEAT_ROWS_MAX][64]
   bf16* x1;                  // [slots][X1_ROWS_MAX][X1_ROW]
@@ -128,11 +130,13 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
     __half* pre = a.pre + (size_t)slot * HOP;
     const int* pcm = a.pcm + (size_t)b * C;
-    for (int i = tid; i < UH; i += BEGIN_THREADS) {
-      __half v = __float2half_rn(0.f);
-      if (i < HOP) v = pre[i];
-      else if (i < C + HOP) v = __float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f);
-      uh[i] = v;
+    if (!a.feats_in) {
+      for (int i = tid; i < UH; i += BEGIN_THREADS) {
+        __half v = __float2half_rn(0.f);
+        if (i < HOP) v = pre[i];
+        else if (i < C + HOP) v = __float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f);
+        uh[i] = v;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -150,12 +154,21 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
       a.len_in[b] = len;
       a.mhsa_len[slot] = min(len + a.T, MHSA_S);   // conformer_blocks.py:191
     }
-    for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = uh[C + i];
+    if (!a.feats_in)
+      for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = uh[C + i];
   }
   if (threadIdx.x == 0) PROF_MARK(1);
 
+  if (a.feats_in) {   // features come from outside: [64][F] fp16 -> featS[f][m]
+    const __half* fi = a.feats_in + (size_t)b * N_MELS * F;
+    for (int i = tid; i < F * N_MELS; i += BEGIN_THREADS) {
+      const int m = i / F, f = i - m * F;
+      featS[f * N_MELS + m] = __half2float(fi[i]);
+    }
+    __syncthreads();
+  }
   // ---- framed DFT on the tensor cores: warp w owns n-tiles w, w+11 (21 tiles of 8 columns)
-  {
+  if (!a.feats_in) {
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     for (int nt = warp; nt < BASIS_N / 8; nt += BEGIN_THREADS / 32) {
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   __syncthreads();
   if (threadIdx.x == 0) PROF_MARK(3);
   // ---- power -> mel -> log (feats.py:99-101)
-  for (int i = tid; i < F * N_MELS; i += BEGIN_THREADS) {
+  for (int i = tid; i < (a.feats_in ? 0 : F * N_MELS); i += BEGIN_THREADS) {
     const int f = i / N_MELS, m = i - f * N_MELS;
     const float* sp = spec + f * 162;
     float e = 0.f;

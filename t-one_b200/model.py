@@ -28,7 +28,7 @@ SYMBOLS = (
     "tone_create", "tone_destroy", "tone_get_info", "tone_last_error", "tone_load_weight",
     "tone_finalize_weights", "tone_alloc_slots", "tone_release_slots", "tone_reset_slots", "tone_step",
     "tone_stage", "tone_step_staged", "tone_fetch", "tone_fetch_greedy", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
-    "tone_import_state", "tone_step_debug", "tone_selftest_gemm", "tone_cluster_prof_read",
+    "tone_import_state", "tone_step_debug", "tone_selftest_gemm", "tone_cluster_prof_read", "tone_step_features",
 )
 
 
@@ -193,6 +193,18 @@ class Engine:
         tk = np.empty((B, self.T), dtype=np.int32)
         self._ck(self._lib.tone_step(self._h, B, _i32p(s), _i32p(x), _f32p(lp), _i32p(tk) if want_tokens else None))
         return lp, tk
+
+    def step_features(self, slots, feats, want_tokens: bool = True):
+        """Feature-input mode (reference ``skip_preprocessor=True``): feats (B, 64, F) log-mel, rounded to fp16."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        f = np.ascontiguousarray(feats, dtype=np.float16)
+        B = len(s)
+        if f.shape != (B, 64, self.chunk_samples // 80):
+            raise ValueError(f"feats must have shape {(B, 64, self.chunk_samples // 80)}, got {f.shape}")
+        lp = np.empty((B, self.T, 35), dtype=np.float32)
+        tk = np.empty((B, self.T), dtype=np.int32)
+        self._ck(self._lib.tone_step_features(self._h, B, _i32p(s), f.ctypes.data_as(C.c_void_p), _f32p(lp), _i32p(tk)))
+        return (lp, tk) if want_tokens else lp
 
     def step_debug(self, slots, pcm):
         s = np.ascontiguousarray(slots, dtype=np.int32)

@@ -72,6 +72,30 @@ def reference_stream(weights, pcm_chunks, mode="fp32"):
     return outs, state
 
 
+def reference_feature_stream(weights, feat_chunks):
+    """The reference's feature-input mode (skip_preprocessor=True, tone/nn/model.py:151-160): feat_chunks is a list of
+    (B,64,F) float arrays; `length` = F frames for every stream.  Returns the list of logprobs and the final state."""
+    Tone, ToneConfig = import_reference_model()
+    cfg = ToneConfig()
+    model = Tone(cfg.feature_extraction_params, cfg.encoder_params, cfg.decoder_params, skip_preprocessor=True).eval()
+    sd = {k: torch.from_numpy(v) for k, v in weights.items()}
+    model.load_state_dict(sd, strict=False)
+    # the reference casts the features to fp16 (model.py:154), so this mode only runs the way it is exported:
+    # fp16 states under fp16 autocast (export.py:411,454-455)
+    B = feat_chunks[0].shape[0]
+    state = model.get_initial_state(batch_size=B, dtype=torch.float16, len_dtype=torch.int64, device="cpu")
+    outs = []
+    with torch.no_grad():
+        for f in feat_chunks:
+            x = torch.from_numpy(f.astype(np.float32))
+            length = torch.full((B,), x.shape[2], dtype=torch.int64)
+            with torch.amp.autocast("cpu", dtype=torch.float16):
+                res = model.forward_for_export(x, length, *state)
+            state = tuple(s.half() if s.is_floating_point() else s for s in res[1:])
+            outs.append(res[0].float().numpy())
+    return outs, state
+
+
 def synth_pcm(B, n_samples, seed=1234):
     tone_b200 = importlib.import_module("t-one_b200")
     return tone_b200.synth.telephony_pcm(B, n_samples, seed)
@@ -103,5 +127,35 @@ def main():
         print(path, os.path.getsize(path) // 1024, "KiB", "logprobs", blob["logprobs"].shape)
 
 
+def main_features():
+    """features_300ms.npz: log-mel features (made by the oracle's frontend from synthetic audio, stored fp16) and what the
+    reference computes from them in feature-input mode."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tone_oracle as orc
+    tone_b200 = importlib.import_module("t-one_b200")
+    weights = tone_b200.weights.init_weights(seed=0)
+    B, C, n_chunks = 2, 2400, 4
+    pcm = synth_pcm(B, C * n_chunks, seed=4321)
+    pre = torch.zeros(B, 80)
+    feats = []
+    for i in range(n_chunks):
+        f, pre = orc.frontend(torch.from_numpy(pcm[:, i * C:(i + 1) * C].astype(np.int32)), pre)
+        feats.append(f.transpose(1, 2).numpy().astype(np.float16))          # (B,64,F)
+    outs, state = reference_feature_stream(weights, feats)
+    blob = {
+        "weights_digest": np.frombuffer(tone_b200.weights.digest(weights).encode(), dtype=np.uint8),
+        "feats": np.stack(feats, 0),                                          # (n,B,64,F) fp16
+        "logprobs": np.stack(outs, 0).astype(np.float32),
+        "state_mhsa_len": state[3].numpy().astype(np.int64),
+    }
+    path = os.path.join(HERE, "features_300ms.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB", "logprobs", blob["logprobs"].shape)
+
+
 if __name__ == "__main__":
-    main()
+    if "--features" in sys.argv:
+        main_features()
+    else:
+        main()
+        main_features()

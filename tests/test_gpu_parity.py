@@ -169,6 +169,29 @@ def test_cluster_path_agrees_with_kernel_path_over_many_chunks(weights, tb):
     assert np.abs(outs[0][1] - outs[1][1]).max() <= ST_TOL
 
 
+def test_feature_input_mode(engines, weights, tb):
+    """tone_step_features (reference skip_preprocessor=True): CUDA vs the oracle's feature path and vs the reference's
+    own outputs (tests/golden/features_300ms.npz, export-mode reference: fp16-autocast spread on top of ours)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "features_300ms.npz"))
+    n, B = g["feats"].shape[:2]
+    eng = engines(2400)
+    W = orc.to_torch(weights)
+    slots = eng.alloc_slots(B)
+    try:
+        st = orc.zero_state(B)
+        for i in range(n):
+            lp, tk = eng.step_features(slots, g["feats"][i])
+            ref, st = orc.step(W, None, st, feats=torch.from_numpy(g["feats"][i].astype(np.float32)))
+            assert np.abs(lp - ref.numpy()).max() <= LP_TOL
+            assert np.abs(lp - g["logprobs"][i]).max() <= LP_TOL
+            _check_tokens(tk, ref.numpy())
+        with pytest.raises(ValueError):
+            eng.step_features(slots, g["feats"][0][:, :, :-1])
+    finally:
+        eng.release_slots(slots)
+
+
 def test_simt_debug_path_agrees(engines, tb):
     """The SIMT debug GEMMs and the tcgen05 GEMMs see the same packed operands: results agree tightly."""
     C, B = 2400, 3

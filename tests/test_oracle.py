@@ -122,3 +122,19 @@ def test_oracle_matches_live_reference(tb, weights):
     outs, _ = mg.reference_stream(weights, chunks, "fp32")
     lp, _ = _run(orc.to_torch(weights), pcm, 2400)
     np.testing.assert_allclose(lp, np.stack(outs, 0), atol=1e-4, rtol=0)
+
+
+def test_feature_input_mode_matches_reference_skip_preprocessor(weights):
+    """Feature-input mode (reference skip_preprocessor=True, tone/nn/model.py:151-160).  The reference only runs this
+    mode the way it is exported (fp16 features -> fp16 autocast), so the bar is the fp16-autocast spread measured on the
+    audio goldens (1.8e-2 between their fp32 and export-mode logprobs), not the 1e-4 of the fp32 goldens."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "features_300ms.npz"))
+    W = orc.to_torch(weights)
+    st = orc.zero_state(g["feats"].shape[1])
+    pre0 = st["preproc"].clone()
+    for i in range(g["feats"].shape[0]):
+        lp, st = orc.step(W, None, st, feats=torch.from_numpy(g["feats"][i].astype(np.float32)))
+        assert np.abs(lp.numpy() - g["logprobs"][i]).max() <= 3e-2
+    assert (st["mhsa_len"].numpy().ravel() == g["state_mhsa_len"].ravel()).all()
+    assert torch.equal(st["preproc"], pre0)          # the waveform state is not touched in this mode
