@@ -96,6 +96,7 @@ struct LayerW {
   float *n_ff1, *n_att, *n_conv, *n_ff2, *n_out;
   float *qln_w, *qln_b, *kln_w, *kln_b;
   float *dw_w, *dw_b;
+  CUtensorMap wv48;     // score-sharing layers: Wv with a 48-row box (one head per N tile of the fused V + P.V kernel)
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -176,6 +177,7 @@ struct tone_engine {
   // conv module's GLU GEMM + depthwise conv in one kernel (TONE_FUSE_DW=1).  Correct but measured SLOWER on B200
   // (19.9 us vs 3.8 + 7.0 us): four epilogue warps per CTA cannot keep enough cache-column loads in flight.
   bool fuse_dw = false;
+  bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel (TONE_FUSE_VATT=0: two kernels)
   int num_sms = 148;
 
   // latency path: the 16 layers + decoder as one thread-block-cluster kernel (encoder_cluster.cuh)
@@ -303,6 +305,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("TONE_PDL")) e->pdl = atoi(v) != 0;
   if (const char* v = getenv("TONE_FUSE_DW")) e->fuse_dw = atoi(v) != 0;
+  if (const char* v = getenv("TONE_FUSE_VATT")) e->fuse_vatt = atoi(v) != 0;
   e->C = cfg->chunk_samples;
   e->F = e->C / HOP;
   e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
@@ -423,6 +426,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
   CK((configure_gemm_tc<G_GLU_DW, BN_GLU>()));
+  CK((configure_gemm_tc<G_VATT, D_HEAD>()));
   CK((configure_gemm_tc<G_RESID, 128>()));
   CK((configure_gemm_tc<G_GLU, 128>()));
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
@@ -723,6 +727,7 @@ static int finalize_layer(tone_engine* e, int l) {
   } else {
     if ((rc = upload_mat(e, wv->data, D_MODEL, D_MODEL, BN_STORE, &L.qkv))) return rc;
     if ((rc = upload_f32(e, bv->data, &L.qkv_b))) return rc;
+    if ((rc = make_map_2d(e, &L.wv48, L.qkv.ptr, D_MODEL, D_MODEL, D_HEAD, true))) return rc;
   }
   // conv module: pw1 rows [0,384) = a, [384,768) = b (GLU = a * sigmoid(b), conformer_blocks.py:422)
   const std::string Cp = Lp + "conv.";
@@ -1246,6 +1251,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     at.len_in = ln.len_in;
     at.T = Tl;
     at.recompute = RECOMPUTE[l] ? 1 : 0;
+    bool fused_att = false;
     if (l < 14) {
       RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
@@ -1262,6 +1268,25 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
         at.q_ln_b = L.qln_b;
         at.k_ln_w = L.kln_w;
         at.k_ln_b = L.kln_b;
+      } else if (e->cfg.gemm_impl == 0 && e->fuse_vatt && M < BIG_M) {
+        // score-sharing layer: ctx = P (n Wv^T + bv) per head in ONE kernel; tiles = whole streams x one head
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.M = B;
+        a.nk = D_MODEL / 64;
+        a.R = Tl;
+        a.G = 128 / Tl;
+        a.out = ln.ctx;
+        a.ldo = D_MODEL;
+        a.bias = L.qkv_b;
+        a.P = ln.P;
+        a.A = ln.n;
+        a.lda = D_MODEL;
+        cudaError_t err = launch_gemm_tc<G_VATT, D_HEAD>(st, ln.m_n, ln.m_n, L.wv48, a, (B + a.G - 1) / a.G, N_HEADS, e->pdl,
+                                                         e->num_sms);
+        e->launches++;
+        if (err != cudaSuccess) return fail(TONE_ECUDA, "fused V + attention launch: %s", cudaGetErrorString(err));
+        fused_att = true;
       } else {
         GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, D_MODEL, L.qkv_b, 1.f);
         if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.qkv, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
@@ -1306,7 +1331,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.k_ln_b = L.kln_b;
       at.mask_mode = (l == 14) ? 2 : 1;
     }
-    if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), 0, st, e->pdl, at));
+    if (fused_att) {
+    } else if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), 0, st, e->pdl, at));
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
     RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));

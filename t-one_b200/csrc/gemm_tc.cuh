@@ -19,6 +19,7 @@ namespace tone {
 
 constexpr int GEMM_THREADS = 320;
 constexpr int EPI_THREADS = 256;
+constexpr int VATT_MAX_T = 13;   // most frames per stream and step (400 ms chunks)
 
 enum GemmKind : int {
   G_STORE_F32 = 0,  // out fp32 = acc + bias                                 (q/k/v, out-linear, reduction pw)
@@ -31,6 +32,8 @@ enum GemmKind : int {
   G_DECODER = 7,    // logprobs = log_softmax(acc + bias)[0:35], argmax      (BN = 48)
   G_PARTIAL = 8,    // part[z] fp16 (saturating) = acc over K slice z (split-K; blockIdx.z)  (ff down; the norm kernel sums
                     // the slices in fp32 in a fixed order)
+  G_VATT = 10,      // score-sharing attention layers in one kernel: v = acc + b for one head (BN = 48) of whole streams,
+                    // then ctx bf16 = P v with the probabilities P published by the last recompute layer
   G_GLU_DW = 9,     // conv module in one kernel: GLU epilogue, then the causal depthwise conv k=31 + BN + SiLU over
                     // [30-row cache | T new rows] per stream and channel, cache roll included (tiles hold whole streams)
 };
@@ -48,6 +51,7 @@ struct GemmArgs {
   float scale;
   long long out_slot_stride;  // G_CONV0: elements between consecutive slots of x1
   int out_row_off;            // G_CONV0: first row written inside a slot (the cached rows come first)
+  const float* P;             // G_VATT: [streams][8][R][R] attention probabilities (R = frames per stream at this rate)
   int* tokens;                // G_DECODER: argmax per frame
   float* aux;                 // G_DECODER: [rows][2] = logprob of ' ' (33) and of blank (34), what the phrase splitter needs
   long long z_stride;         // G_PARTIAL: elements between the partial outputs of consecutive K slices
@@ -78,7 +82,7 @@ template <int KIND>
 struct KindTraits {
   static constexpr bool gather = (KIND == G_CONV0 || KIND == G_CONV1 || KIND == G_KV);
   // rows of a tile are G whole streams x R frames (gather kinds, and dense kinds that need whole streams per tile)
-  static constexpr bool stream_rows = gather || (KIND == G_GLU_DW);
+  static constexpr bool stream_rows = gather || (KIND == G_GLU_DW) || (KIND == G_VATT);
 };
 
 // DEEP = one CTA per SM with the whole shared memory as the operand ring: the small-batch GEMMs of this model are
@@ -218,6 +222,80 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
       if (a.tokens) a.tokens[ri.out_row] = am;
       if (a.aux) *reinterpret_cast<float2*>(a.aux + ri.out_row * 2) = make_float2(lg[33] - lse, lg[34] - lse);
+    }
+    return;
+  } else if constexpr (KIND == G_VATT) {
+    // Tile = G whole streams x R frames (rows), one head (48 columns).  Phase 1: v rows (+ bias) -> fp32 staging.
+    // Phase 2: unit = (row, 8 dims): ctx[t][d] = sum_j P[t][j] v[j][d] over the R rows of the row's stream.
+    static_assert(KIND != G_VATT || BN == 48, "one head per tile");
+    constexpr int VLD = 52;                              // floats per staged v row (16 B aligned, conflict-light)
+    const int R = a.R, head = blockIdx.y;
+    float* vst = reinterpret_cast<float*>(stage);
+    // P rows of this thread's units, fetched before the accumulator is ready (they come from an earlier layer)
+    constexpr int NU = 3;                                // units per thread: 128 rows x 6 / 256 threads
+    const int et = (threadIdx.x - 64);
+    float pr[NU][VATT_MAX_T];
+    int urow[NU], uu[NU];
+    bool uok[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int unit = et + k * EPI_THREADS;
+      urow[k] = unit / 6;
+      uu[k] = unit - urow[k] * 6;
+      const RowInfo ri = row_info<KIND>(a, urow[k] < 128 ? urow[k] : 0);
+      uok[k] = urow[k] < 128 && ri.valid;
+      if (uok[k]) {
+        const int b = (int)(ri.out_row / R), t = (int)(ri.out_row - (long long)b * R);
+        const float* pp = a.P + (((size_t)b * 8 + head) * R + t) * R;
+#pragma unroll
+        for (int j = 0; j < VATT_MAX_T; ++j) pr[k][j] = j < R ? __ldg(pp + j) : 0.f;
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) PROF_MARK(4);
+    tc_fence_after();
+    {
+      // 24 columns per half: two 16-wide TMEM loads (the second overlaps into the other half, 8 used)
+      uint32_t r0[16], r1[16];
+      tmem_ld16_async(tmem_row_base + 24 * hf, r0);
+      tmem_ld16_async(tmem_row_base + 24 * hf + 16, r1);
+      tmem_ld_wait();
+      tmem_regs_ready16(r0);
+      tmem_regs_ready16(r1);
+      float* vr = vst + (q * 32 + lane) * VLD + 24 * hf;
+#pragma unroll
+      for (int c = 0; c < 24; c += 4) {
+        float4 o;
+        o.x = __uint_as_float(c < 16 ? r0[c] : r1[c - 16]) + s_c0[24 * hf + c];
+        o.y = __uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]) + s_c0[24 * hf + c + 1];
+        o.z = __uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]) + s_c0[24 * hf + c + 2];
+        o.w = __uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]) + s_c0[24 * hf + c + 3];
+        *reinterpret_cast<float4*>(vr + c) = o;
+      }
+    }
+    bar_epilogue();
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      if (!uok[k]) continue;
+      const int g = urow[k] / R;                          // stream within the tile
+      const float* vb = vst + (g * R) * VLD + uu[k] * 8;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < VATT_MAX_T; ++j) {
+        if (j < R) {
+          const float4 v0 = *reinterpret_cast<const float4*>(vb + j * VLD);
+          const float4 v1 = *reinterpret_cast<const float4*>(vb + j * VLD + 4);
+          const float p = pr[k][j];
+          acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
+          acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+        }
+      }
+      const RowInfo ri = row_info<KIND>(a, urow[k]);
+      bf16* dst = reinterpret_cast<bf16*>(a.out) + ri.out_row * (long long)a.ldo + head * 48 + uu[k] * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
     }
     return;
   } else if constexpr (KIND == G_GLU_DW) {
@@ -570,7 +648,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(con
           for (int g = 0; g < nvalid; ++g)
             tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
       } else {
-        tma_load_2d(dA, &tmA, &full[s], kz + it * 64, (KIND == G_GLU_DW) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
+        tma_load_2d(dA, &tmA, &full[s], kz + it * 64,
+                    (KIND == G_GLU_DW || KIND == G_VATT) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
       }
     };
     if (lane < npre) load_a(lane, lane);
