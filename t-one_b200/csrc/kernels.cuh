@@ -79,18 +79,26 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   float* spec = reinterpret_cast<float*>(uh + ((UH + 7) & ~7));   // [F][162]
   float* featS = spec + F * 162;                        // [F][64]
   const int b = blockIdx.x, tid = threadIdx.x;
-  {  // constant basis -> smem, before the PDL wait (it does not depend on the previous kernel)
-    const uint4* src = reinterpret_cast<const uint4*>(a.basis);
-    uint4* dst = reinterpret_cast<uint4*>(basisS);
-    constexpr int N16 = 2 * BASIS_N * BASIS_LD * 2 / 16;   // 7056
-    for (int i0 = 0; i0 < N16; i0 += 4 * BEGIN_THREADS) {
-      uint4 t[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (i0 + q * BEGIN_THREADS + tid < N16) t[q] = __ldg(src + i0 + q * BEGIN_THREADS + tid);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (i0 + q * BEGIN_THREADS + tid < N16) dst[i0 + q * BEGIN_THREADS + tid] = t[q];
+  // constant basis -> smem by ONE bulk async copy (113 KB), issued before the PDL wait and awaited just before the DFT;
+  // the mel filterbank (CSR, ~1 KB) is staged the same way so that the mel loop does not chase indices in global memory
+  __shared__ uint64_t basis_bar;
+  __shared__ int mel_startS[N_MELS + 1];
+  __shared__ unsigned char mel_binS[256];
+  __shared__ float mel_wS[256];
+  constexpr uint32_t BASIS_BYTES = 2 * BASIS_N * BASIS_LD * 2;
+  static_assert(BASIS_BYTES % 16 == 0, "bulk copy granularity");
+  if (tid == 0) {
+    mbar_init(&basis_bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(&basis_bar, BASIS_BYTES);
+    bulk_load_1d(basisS, a.basis, BASIS_BYTES, &basis_bar);
+  }
+  if (tid <= N_MELS) mel_startS[tid] = a.mel_start[tid];
+  {
+    const int nnz = a.mel_start[N_MELS];
+    for (int i = tid; i < nnz && i < 256; i += BEGIN_THREADS) {
+      mel_binS[i] = a.mel_bin[i];
+      mel_wS[i] = a.mel_w[i];
     }
   }
   pdl_wait();
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     __syncthreads();
   }
   // ---- framed DFT on the tensor cores: warp w owns n-tiles w, w+11 (21 tiles of 8 columns)
+  mbar_wait(&basis_bar, 0);
   if (!a.feats_in) {
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -212,10 +221,10 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     const int f = i / N_MELS, m = i - f * N_MELS;
     const float* sp = spec + f * 162;
     float e = 0.f;
-    for (int p = a.mel_start[m]; p < a.mel_start[m + 1]; ++p) {
-      const int kb = a.mel_bin[p];
+    for (int p = mel_startS[m]; p < mel_startS[m + 1]; ++p) {
+      const int kb = mel_binS[p];
       const float re = sp[kb], im = sp[N_BINS + kb];
-      e = fmaf(a.mel_w[p], re * re + im * im, e);
+      e = fmaf(mel_wS[p], re * re + im * im, e);
     }
     featS[i] = logf(e + 5.9604644775390625e-08f);   // 2^-24
   }
