@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 tb = importlib.import_module("t-one_b200")
 
 NAMES = {1: "begin_step", 2: "norm", 3: "upsample_norm", 4: "attention", 5: "dwconv", 6: "reduction_dw"}
-KINDS = ["store_f32", "resid", "swiglu", "glu", "conv0", "conv1", "kv", "decoder", "partial", "glu_dw"]
+KINDS = ["store_f32", "resid", "swiglu", "glu", "conv0", "conv1", "kv", "decoder", "partial", "glu_dw", "vatt"]
 
 
 def name(i):
