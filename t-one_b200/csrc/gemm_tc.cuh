@@ -665,24 +665,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(BN);
-      for (int it = 0; it < a.nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        if (it == 0) PROF_MARK(3);      // first operand stage landed
-        tc_fence_after();
-        const uint64_t da = make_sw128_desc(smem_u32(sA + s * Cfg::A_BYTES));
-        const uint64_t db = make_sw128_desc(smem_u32(sB + s * Cfg::B_BYTES));
+    // ---------------- MMA issuer: the whole warp walks the K loop (warp-uniform control flow and descriptors), one
+    // elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(BN);
+    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    for (int it = 0; it < a.nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      if (it == 0 && lane == 0) PROF_MARK(3);      // first operand stage landed
+      tc_fence_after();
+      const uint64_t da = make_sw128_desc(sA_u32 + s * Cfg::A_BYTES);
+      const uint64_t db = make_sw128_desc(sB_u32 + s * Cfg::B_BYTES);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle atom
           umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
       }
-      umma_commit(tmem_full);        // accumulator complete
+      __syncwarp();
     }
+    if (elect_one_sync()) umma_commit(tmem_full);        // accumulator complete
+    __syncwarp();
   } else {
     // ---------------- epilogue: warps 2..9; warp w owns TMEM lanes 32*(w%4) .. +31, column half (w-2)/4
     const int q = warp & 3, hf = (warp - 2) >> 2;
