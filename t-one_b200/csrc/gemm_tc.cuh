@@ -654,15 +654,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(con
     };
     if (lane < npre) load_a(lane, lane);
     __syncwarp();
-    if (lane == 0) {
-      for (int it = npre; it < a.nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    // steady state (ring wraps): warp-uniform loop, one elected lane issues (operands stay in uniform registers)
+    for (int it = npre; it < a.nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(&full[s], a_bytes + Cfg::B_BYTES);
         tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full[s], kz + it * 64, b_row);
         load_a(it, s);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: the whole warp walks the K loop (warp-uniform control flow and descriptors), one
