@@ -15,7 +15,7 @@
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap tm, int mode, int rows_per_tile,
-                                             int nt, long long* out) {
+                                             int nt, long long* out, int nbox = 6) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar[6];
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
   }
   __syncthreads();
   long long t0 = 0, t1 = 0, tfirst = 0;
-  if (threadIdx.x < 6) {
+  if (threadIdx.x < nbox) {
     const int kb = threadIdx.x;
     // mode 0 (shared): tile m; mode 1 (distinct): tile blockIdx.x; mode 2 (panel): rows of panel kb
     int x = kb * 64, y = (mode == 1 ? blockIdx.x : m) * rows_per_tile;
@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
       x = 0;
       y = kb * (gridDim.x / nt) * rows_per_tile + m * rows_per_tile;
     }
-    __syncwarp(0x3f);
+    const unsigned lm = (1u << nbox) - 1u;
+    __syncwarp(lm);
     t0 = clock64();
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[kb])), "r"(16384) : "memory");
     asm volatile(
@@ -53,9 +54,9 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
     long long d = t1 - t0;
     long long dmax = d, dmin = d;
     for (int o = 4; o > 0; o >>= 1) {
-      long long a = __shfl_xor_sync(0x3f, dmax, o), b = __shfl_xor_sync(0x3f, dmin, o);
-      // lanes 6,7 do not exist in the mask: guard by lane id
-      if ((threadIdx.x ^ o) < 6) {
+      if ((int)(threadIdx.x ^ o) >= nbox && nbox != 6) continue;   // partner not in the mask (nbox = 1, 2, 3: handled below)
+      long long a = __shfl_xor_sync(lm, dmax, o), b = __shfl_xor_sync(lm, dmin, o);
+      if ((int)(threadIdx.x ^ o) < nbox) {
         dmax = a > dmax ? a : dmax;
         dmin = b < dmin ? b : dmin;
       }
@@ -120,6 +121,23 @@ int main() {
     std::sort(maxs.begin(), maxs.end());
     printf("%-24s CTAs %3d: first box median %.2f us | last box median %.2f us, p95 %.2f us, max %.2f us\n", c.name, grid,
            mins[mins.size() / 2], maxs[maxs.size() / 2], maxs[maxs.size() * 95 / 100], maxs.back());
+  }
+  // bytes vs time: 1, 2, 3 and 6 boxes of 16 KB per CTA, 60 CTAs (5 tiles x 12)
+  for (int nbox : {1, 2, 6}) {
+    const int grid = 60;
+    std::vector<long long> h(2 * grid);
+    std::vector<double> maxs;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaMemset(A, rep, (size_t)5 * TILE * K * 2);
+      ingest<<<grid, 64, 100 * 1024>>>(rowmajor, 0, TILE, 12, out, nbox);
+      cudaDeviceSynchronize();
+      cudaMemcpy(h.data(), out, 2 * grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      if (rep == 0) continue;
+      for (int i = 0; i < grid; ++i) maxs.push_back(h[2 * i + 1] / 1965.0);
+    }
+    std::sort(maxs.begin(), maxs.end());
+    printf("boxes per CTA %d (%3d KB): last box median %.2f us, p95 %.2f us\n", nbox, nbox * 16, maxs[maxs.size() / 2],
+           maxs[maxs.size() * 95 / 100]);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) printf("error: %s\n", cudaGetErrorString(e));
