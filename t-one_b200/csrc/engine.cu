@@ -1537,8 +1537,50 @@ extern "C" int tone_sync(tone_engine* e) {
   return TONE_OK;
 }
 
+// One graph for the whole host-facing call: H2D of slots + PCM from the pinned staging buffers, the step, D2H of
+// logprobs + tokens into the pinned staging buffers (one launch and one synchronise instead of six API calls).
+static int launch_step_e2e(tone_engine* e, int B) {
+  const int key = B + (2 << 24);
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t c1 = cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream);
+    cudaError_t c2 = cudaMemcpyAsync(e->d_pcm, e->p_pcm, (size_t)B * e->C * 4, cudaMemcpyHostToDevice, e->stream);
+    int rc = enqueue_step(e, B, e->stream, nullptr, false);
+    cudaError_t c3 = cudaMemcpyAsync(e->p_logprobs, e->logprobs, (size_t)B * e->T * N_CLASSES * 4, cudaMemcpyDeviceToHost,
+                                     e->stream);
+    cudaError_t c4 = cudaMemcpyAsync(e->p_tokens, e->d_tokens, (size_t)B * e->T * 4, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) return rc;
+    if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess || ce != cudaSuccess)
+      return fail(TONE_ECUDA, "graph capture (host-facing step): %s", cudaGetErrorString(ce != cudaSuccess ? ce : c1));
+    cudaGraphExec_t exec;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    it = e->graphs.emplace(key, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, e->stream));
+  return 0;
+}
+
 extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
                          int32_t* tokens) {
+  if (e && e->cfg.use_graph) {
+    RC(check_step_args(e, B));
+    if (!slots || !pcm) return fail(TONE_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    for (int i = 0; i < B; ++i)
+      if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
+        return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
+    if (slots != e->p_slots) memcpy(e->p_slots, slots, (size_t)B * 4);
+    if (pcm != e->p_pcm) memcpy(e->p_pcm, pcm, (size_t)B * e->C * 4);
+    RC(launch_step_e2e(e, B));
+    CK(cudaStreamSynchronize(e->stream));
+    if (logprobs && logprobs != e->p_logprobs) memcpy(logprobs, e->p_logprobs, (size_t)B * e->T * N_CLASSES * 4);
+    if (tokens && tokens != e->p_tokens) memcpy(tokens, e->p_tokens, (size_t)B * e->T * 4);
+    return TONE_OK;
+  }
   RC(tone_stage(e, B, slots, pcm));
   RC(launch_step(e, B, e->stream));
   return tone_fetch(e, B, logprobs, tokens);
