@@ -177,6 +177,14 @@ struct tone_engine {
   // conv module's GLU GEMM + depthwise conv in one kernel (TONE_FUSE_DW=1).  Correct but measured SLOWER on B200
   // (19.9 us vs 3.8 + 7.0 us): four epilogue warps per CTA cannot keep enough cache-column loads in flight.
   bool fuse_dw = false;
+  // Large dense GEMMs (>= persist_min_tiles output tiles) run as a persistent one-CTA-per-SM kernel with the epilogue
+  // overlapped with the next tile's main loop (gemm_tc_persist_kernel); 0 = never.
+  // (default: more tiles than SMs, set in tone_create).  TONE_PERSIST_MIN_TILES / TONE_PERSIST_MODE override.
+  int persist_min_tiles = 0, persist_ctas = 0;
+  // gated kinds (N % 256 == 0): 0 = 128-wide tiles, 1 = 256-wide, 2 = 256-wide on CTA pairs (cta_group::2).  Measured
+  // (profiles/r01_persistent_gemm.md): the pair form runs the feed-forward up GEMM at 73 % of the sustained bf16 peak when
+  // it has the GPU to itself, but with two lanes in flight the 256-wide single-CTA form gives the faster step.
+  int persist_mode = 1;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel (TONE_FUSE_VATT=0: two kernels)
   int num_sms = 148;
 
@@ -306,6 +314,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   if (const char* v = getenv("TONE_PDL")) e->pdl = atoi(v) != 0;
   if (const char* v = getenv("TONE_FUSE_DW")) e->fuse_dw = atoi(v) != 0;
   if (const char* v = getenv("TONE_FUSE_VATT")) e->fuse_vatt = atoi(v) != 0;
+  if (const char* v = getenv("TONE_PERSIST_MODE")) e->persist_mode = atoi(v);
   e->C = cfg->chunk_samples;
   e->F = e->C / HOP;
   e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
@@ -429,6 +438,19 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_VATT, D_HEAD>()));
   CK((configure_gemm_tc<G_RESID, 128>()));
   CK((configure_gemm_tc<G_GLU, 128>()));
+  CK((configure_gemm_tc_persist<G_SWIGLU, 1, false>()));
+  CK((configure_gemm_tc_persist<G_SWIGLU, 2, false>()));
+  CK((configure_gemm_tc_persist<G_SWIGLU, 2, true>()));
+  CK((configure_gemm_tc_persist<G_GLU, 1, false>()));
+  CK((configure_gemm_tc_persist<G_GLU, 2, false>()));
+  CK((configure_gemm_tc_persist<G_GLU, 2, true>()));
+  CK((configure_gemm_tc_persist<G_RESID, 1, false>()));
+  CK((configure_gemm_tc_persist<G_STORE_F32, 1, false>()));
+  CK((configure_gemm_tc_persist<G_PARTIAL, 1, false>()));
+  e->persist_ctas = e->num_sms;
+  e->persist_min_tiles = e->num_sms + 1;
+  if (const char* v = getenv("TONE_PERSIST_CTAS")) e->persist_ctas = std::max(2, atoi(v));
+  if (const char* v = getenv("TONE_PERSIST_MIN_TILES")) e->persist_min_tiles = atoi(v);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
   *out = e;
@@ -1031,7 +1053,22 @@ static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const W
   a.W = w.ptr;
   a.ldw = w.K;
   cudaError_t err;
-  if (e->cfg.gemm_impl == 0)
+  constexpr bool can_persist = BN == 128 && (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_RESID || KIND == G_STORE_F32 ||
+                                             KIND == G_PARTIAL);
+  bool persist = false;
+  if constexpr (can_persist)
+    persist = e->cfg.gemm_impl == 0 && splits == 1 && e->persist_min_tiles > 0 && m_tiles * n_tiles >= e->persist_min_tiles;
+  if (persist) {
+    if constexpr (can_persist) {
+      const CUtensorMap& mb = box128 ? w.map128 : w.map;
+      constexpr bool wide = (KIND == G_SWIGLU || KIND == G_GLU);   // N a multiple of 256: two weight tiles per tile
+      if (wide && e->persist_mode == 2)
+        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, wide>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
+      else if (wide && e->persist_mode == 1)
+        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
+      else err = launch_gemm_tc_persist<KIND, 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
+    }
+  } else if (e->cfg.gemm_impl == 0)
     err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, box128 ? w.map128 : w.map, a, m_tiles, n_tiles, e->pdl,
                                    e->num_sms, splits);
   else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols, splits);

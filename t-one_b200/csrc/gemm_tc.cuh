@@ -553,6 +553,448 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
   }
 }
 
+// ---------------------------------------------------------------------------------------------- persistent-kernel epilogues
+// The same epilogue code with the tile coordinates, the accumulator-barrier parity, the TMEM-release barrier, the
+// named-barrier id and a precomputed row scale as arguments.  Kept as a separate copy so that the one-tile kernel
+// compiles to exactly the code it had before (threading these through the shared functions cost 64 streams 1.3 %).
+template <int KIND, bool PERSIST = true>
+__device__ __forceinline__ RowInfo row_info_p(const GemmArgs& a, int tx, int row_in_tile) {
+  RowInfo ri;
+  if constexpr (KindTraits<KIND>::stream_rows) {
+    int g = row_in_tile / a.R;
+    int j = row_in_tile - g * a.R;
+    int b = tx * a.G + g;
+    ri.valid = (g < a.G) && (b < a.M);
+    if constexpr (KIND == G_CONV0) {
+      int slot = ri.valid ? a.slots[b] : 0;
+      ri.out_row = (long long)slot * a.out_slot_stride + (long long)(a.out_row_off + j) * a.ldo;
+    } else {
+      ri.out_row = (long long)b * a.R + j;
+    }
+  } else {
+    int m = tx * 128 + row_in_tile;
+    ri.valid = m < a.M;
+    ri.out_row = m;
+  }
+  return ri;
+}
+
+template <int KIND, int BN, bool PERSIST = true>
+__device__ __forceinline__ void stage_constants_p(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..255*/, int ty) {
+  const int n0 = ty * BN;
+  if constexpr (KIND == G_PARTIAL) {
+    return;
+  } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
+    constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
+    if (t < BN) {
+      s_c0[t] = __ldg(a.alpha + (n0 + t) % CH);
+      s_c1[t] = __ldg(a.beta + (n0 + t) % CH);
+    }
+  } else if constexpr (KIND == G_DECODER) {
+    if (t < 48) s_c0[t] = t < 35 ? __ldg(a.bias + t) : 0.f;
+  } else if constexpr (KIND == G_GLU_DW) {
+    if (t < BN) s_c0[t] = __ldg(a.bias + n0 + t);
+    // depthwise taps [31][32] + bias [32] of this tile's 32 channels, behind the per-column constants
+    float* wS = s_c1 + 128;
+    for (int i = t; i < 32 * 32; i += EPI_THREADS) {
+      const int j = i >> 5, c = i & 31;
+      wS[i] = (j < 31) ? __ldg(a.dw_w + j * 384 + ty * 32 + c) : __ldg(a.dw_b + ty * 32 + c);
+    }
+  } else {
+    if (t < BN) s_c0[t] = a.bias ? __ldg(a.bias + n0 + t) : 0.f;
+  }
+}
+
+// Named barrier of one epilogue group (ids 1 and 2).
+__device__ __forceinline__ void bar_epilogue_p(int id = 1) {   // immediate barrier ids (the id is a constant after inlining)
+  if (id == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+template <int KIND, int BN, bool PERSIST = true>
+// (tx, ty) = tile coordinates (arguments); par = phase parity of tmem_full;
+// tmem_empty (persistent kernel only): shared::cluster address of the barrier each warp arrives on once its
+// accumulator columns are out of TMEM (0 = none).
+__device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_base, int q, int hf, int lane, char* stage,
+                                         const float* s_c0, const float* s_c1, uint64_t* tmem_full, int tx_in, int ty_in,
+                                         uint32_t par_in = 0, uint32_t tmem_empty_in = 0, int bar_id_in = 1,
+                                         const float* rs_pre_in = nullptr) {
+  using O = OutCfg<KIND, BN>;
+  const int tx = PERSIST ? tx_in : (int)blockIdx.x, ty = PERSIST ? ty_in : (int)blockIdx.y;
+  const uint32_t par = PERSIST ? par_in : 0u, tmem_empty = PERSIST ? tmem_empty_in : 0u;
+  const int bar_id = PERSIST ? bar_id_in : 1;
+  const float* rs_pre = PERSIST ? rs_pre_in : nullptr;
+  const int n0 = ty * BN;
+
+  if constexpr (KIND == G_DECODER) {
+    if (hf) return;
+    const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, q * 32 + lane);
+    float lg[48];
+    mbar_wait(tmem_full, par);
+    if (threadIdx.x == 64) PROF_MARK(4);
+    tc_fence_after();
+    tmem_ld16(tmem_row_base + 0, lg);
+    tmem_ld16(tmem_row_base + 16, lg + 16);
+    tmem_ld16(tmem_row_base + 32, lg + 32);
+    if (ri.valid) {
+      float mx = -INFINITY;
+      int am = 0;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) {
+        lg[i] += s_c0[i];
+        if (lg[i] > mx) {  // strict > keeps the first maximum (numpy argmax, tone/decoder.py:57)
+          mx = lg[i];
+          am = i;
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) sum += expf(lg[i] - mx);
+      const float lse = mx + logf(sum);
+      float* __restrict__ out = reinterpret_cast<float*>(a.out) + ri.out_row * 35;
+#pragma unroll
+      for (int i = 0; i < 35; ++i) out[i] = lg[i] - lse;
+      if (a.tokens) a.tokens[ri.out_row] = am;
+      if (a.aux) *reinterpret_cast<float2*>(a.aux + ri.out_row * 2) = make_float2(lg[33] - lse, lg[34] - lse);
+    }
+    return;
+  } else if constexpr (KIND == G_VATT) {
+    // Tile = G whole streams x R frames (rows), one head (48 columns).  Phase 1: v rows (+ bias) -> fp32 staging.
+    // Phase 2: unit = (row, 8 dims): ctx[t][d] = sum_j P[t][j] v[j][d] over the R rows of the row's stream.
+    static_assert(KIND != G_VATT || BN == 48, "one head per tile");
+    constexpr int VLD = 52;                              // floats per staged v row (16 B aligned, conflict-light)
+    const int R = a.R, head = ty;
+    float* vst = reinterpret_cast<float*>(stage);
+    // P rows of this thread's units, fetched before the accumulator is ready (they come from an earlier layer)
+    constexpr int NU = 3;                                // units per thread: 128 rows x 6 / 256 threads
+    const int et = (threadIdx.x - 64);
+    float pr[NU][VATT_MAX_T];
+    int urow[NU], uu[NU];
+    bool uok[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int unit = et + k * EPI_THREADS;
+      urow[k] = unit / 6;
+      uu[k] = unit - urow[k] * 6;
+      const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, urow[k] < 128 ? urow[k] : 0);
+      uok[k] = urow[k] < 128 && ri.valid;
+      if (uok[k]) {
+        const int b = (int)(ri.out_row / R), t = (int)(ri.out_row - (long long)b * R);
+        const float* pp = a.P + (((size_t)b * 8 + head) * R + t) * R;
+#pragma unroll
+        for (int j = 0; j < VATT_MAX_T; ++j) pr[k][j] = j < R ? __ldg(pp + j) : 0.f;
+      }
+    }
+    mbar_wait(tmem_full, par);
+    if (threadIdx.x == 64) PROF_MARK(4);
+    tc_fence_after();
+    {
+      // 24 columns per half: two 16-wide TMEM loads (the second overlaps into the other half, 8 used)
+      uint32_t r0[16], r1[16];
+      tmem_ld16_async(tmem_row_base + 24 * hf, r0);
+      tmem_ld16_async(tmem_row_base + 24 * hf + 16, r1);
+      tmem_ld_wait();
+      tmem_regs_ready16(r0);
+      tmem_regs_ready16(r1);
+      float* vr = vst + (q * 32 + lane) * VLD + 24 * hf;
+#pragma unroll
+      for (int c = 0; c < 24; c += 4) {
+        float4 o;
+        o.x = __uint_as_float(c < 16 ? r0[c] : r1[c - 16]) + s_c0[24 * hf + c];
+        o.y = __uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]) + s_c0[24 * hf + c + 1];
+        o.z = __uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]) + s_c0[24 * hf + c + 2];
+        o.w = __uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]) + s_c0[24 * hf + c + 3];
+        *reinterpret_cast<float4*>(vr + c) = o;
+      }
+    }
+    bar_epilogue_p(bar_id);
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      if (!uok[k]) continue;
+      const int g = urow[k] / R;                          // stream within the tile
+      const float* vb = vst + (g * R) * VLD + uu[k] * 8;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < VATT_MAX_T; ++j) {
+        if (j < R) {
+          const float4 v0 = *reinterpret_cast<const float4*>(vb + j * VLD);
+          const float4 v1 = *reinterpret_cast<const float4*>(vb + j * VLD + 4);
+          const float p = pr[k][j];
+          acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
+          acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+        }
+      }
+      const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, urow[k]);
+      bf16* dst = reinterpret_cast<bf16*>(a.out) + ri.out_row * (long long)a.ldo + head * 48 + uu[k] * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    }
+    return;
+  } else if constexpr (KIND == G_GLU_DW) {
+    // experimental fused conv module (off by default): one warp per quarter does all columns, then the depthwise stage
+    const int n0_out = ty * (BN / 2);
+    float rs = 1.f;
+    if (a.ss) {
+      const RowInfo rme = row_info_p<KIND, PERSIST>(a, tx, q * 32 + lane);
+      if (rme.valid) {
+        const float* sp = a.ss + rme.out_row * a.ss_ld;
+        float t = 0.f;
+        for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
+        rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
+      }
+    }
+    float dwc[3][30];
+    if (!hf) {
+#pragma unroll
+      for (int si = 0; si < 3; ++si) {
+        const int g = q + 4 * si, b = tx * a.G + g;
+        if (g < a.G && b < a.M) {
+          const bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + ty * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < 30; ++i) dwc[si][i] = __bfloat162float(cache[i * 384]);
+        }
+      }
+    }
+    mbar_wait(tmem_full, par);
+    tc_fence_after();
+    if (!hf) {
+      float acc[BN];
+      tmem_load_row<BN>(tmem_row_base, acc);
+      const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
+      const uint32_t c0a = smem_u32(s_c0);
+      constexpr int HW = BN / 2;
+#pragma unroll
+      for (int c = 0; c < HW; c += 8) {
+        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
+        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fmaf(acc[c + i], rs, gb[i]) * sigmoid_f(fmaf(acc[HW + c + i], rs, ub[i]));
+        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                         pack_bf16x2(r[6], r[7])));
+      }
+    }
+    bar_epilogue_p(bar_id);   // the whole GLU tile is staged
+    if (hf) return;
+    static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
+    const int T = a.R;
+    const int cg = ty * 32 + lane;            // global channel
+    const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
+    const float bias = wS[31 * 32 + lane];
+#pragma unroll
+    for (int si = 0; si < 3; ++si) {
+      const int g = q + 4 * si, b = tx * a.G + g;
+      if (g < a.G && b < a.M) {
+        bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
+        float col[30 + 13];
+#pragma unroll
+        for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
+#pragma unroll
+        for (int t = 0; t < 13; ++t)
+          if (t < T)
+            col[30 + t] = __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
+        float acc2[13];
+#pragma unroll
+        for (int t = 0; t < 13; ++t) acc2[t] = bias;
+#pragma unroll
+        for (int j = 0; j < 31; ++j) {
+          const float wj = wS[j * 32 + lane];
+#pragma unroll
+          for (int t = 0; t < 13; ++t)
+            if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
+        }
+        bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
+#pragma unroll
+        for (int t = 0; t < 13; ++t)
+          if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
+#pragma unroll
+        for (int i = 0; i < 30; ++i) {
+          float vsel = col[i];
+#pragma unroll
+          for (int t = 1; t <= 13; ++t)
+            if (t == T) vsel = col[i + t];
+          cache[i * 384] = __float2bfloat16(vsel);
+        }
+      }
+    }
+    (void)n0_out;
+    return;
+  } else {
+    constexpr bool gated = (KIND == G_SWIGLU || KIND == G_GLU);
+    // element offset of this tile's first output column
+    const int n0_out = gated ? ty * (BN / 2) : n0;
+    // phase-2 geometry (also used to prefetch the residual before the accumulator is ready)
+    const int row0 = q * 32 + hf * 16;                       // first of this warp's 16 write-out rows
+    const int sub_row = lane / O::LPR, cb = (lane % O::LPR) * 16;
+    float4 rres[O::NIT];
+    if constexpr (KIND == G_RESID) {
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, row0 + it * O::RPI + sub_row);
+        if (ri.valid) rres[it] = *reinterpret_cast<const float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb);
+      }
+    }
+    // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
+    float rs = 1.f;
+    if constexpr (gated) {
+      if (rs_pre) {
+        rs = *rs_pre;
+      } else if (a.ss) {
+        const RowInfo rme = row_info_p<KIND, PERSIST>(a, tx, q * 32 + lane);
+        if (rme.valid) {
+          const float* sp = a.ss + rme.out_row * a.ss_ld;
+          float t = 0.f;
+          for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
+          rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);   // 384^-1/2, eps outside the sqrt (submodules.py:50-52)
+        }
+      }
+    }
+    mbar_wait(tmem_full, par);
+    if (threadIdx.x == 64) PROF_MARK(4);
+    tc_fence_after();
+
+    // ---- phase 1: half of the accumulator row -> final-type row in shared memory (all TMEM loads in flight, one wait)
+    const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
+    const uint32_t c0a = smem_u32(s_c0), c1a = smem_u32(s_c1);
+    if constexpr (O::f32) {
+      constexpr int NC = BN / 2;                 // this warp's columns [hf * NC, hf * NC + NC)
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
+#pragma unroll
+      for (int c = 0; c < NC; c += 4) {
+        float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        {
+          const float4 bb = lds128(c0a + (cbase + c) * 4);
+          o.x += bb.x;
+          o.y += bb.y;
+          o.z += bb.z;
+          o.w += bb.w;
+        }
+        if constexpr (KIND == G_RESID) {
+          o.x *= a.scale;
+          o.y *= a.scale;
+          o.z *= a.scale;
+          o.w *= a.scale;
+        }
+        sts128(srow + (cbase + c) * 4, o);
+      }
+    } else if constexpr (gated) {
+      constexpr int HW = BN / 2;  // first half of the tile = gate / a, second half = value / b
+      constexpr int NC = HW / 2;  // this warp's output columns [hf * NC, hf * NC + NC)
+      const int cbase = hf * NC;
+      float ag[NC], av[NC];
+      {
+        uint32_t* rg = reinterpret_cast<uint32_t*>(ag);
+        uint32_t* rv = reinterpret_cast<uint32_t*>(av);
+#pragma unroll
+        for (int c = 0; c < NC; c += 16) {
+          tmem_ld16_async(tmem_row_base + cbase + c, rg + c);
+          tmem_ld16_async(tmem_row_base + HW + cbase + c, rv + c);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; c += 16) {
+          tmem_regs_ready16(rg + c);
+          tmem_regs_ready16(rv + c);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        const float4 g0 = lds128(c0a + (cbase + c) * 4), g1 = lds128(c0a + (cbase + c) * 4 + 16);
+        const float4 u0 = lds128(c0a + (HW + cbase + c) * 4), u1 = lds128(c0a + (HW + cbase + c) * 4 + 16);
+        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = fmaf(ag[c + i], rs, gb[i]), y = fmaf(av[c + i], rs, ub[i]);
+          r[i] = (KIND == G_SWIGLU) ? silu_f(x) * y : x * sigmoid_f(y);
+        }
+        sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                                   pack_bf16x2(r[6], r[7])));
+      }
+    } else if constexpr (KIND == G_PARTIAL) {   // raw K-slice sums as saturating fp16
+      constexpr int NC = BN / 2;
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __half2 hv = __floats2half2_rn(fminf(fmaxf(acc[c + 2 * i], -65504.f), 65504.f),
+                                               fminf(fmaxf(acc[c + 2 * i + 1], -65504.f), 65504.f));
+          pk[i] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        sts128u(srow + (cbase + c) * 2, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+    } else {  // G_CONV0 / G_CONV1: folded BatchNorm + SiLU per output channel
+      constexpr int NC = BN / 2;
+      const int cbase = hf * NC;
+      float acc[NC];
+      tmem_load_row<NC>(tmem_row_base + cbase, acc);
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        const float4 a0 = lds128(c0a + (cbase + c) * 4), a1 = lds128(c0a + (cbase + c) * 4 + 16);
+        const float4 b0 = lds128(c1a + (cbase + c) * 4), b1 = lds128(c1a + (cbase + c) * 4 + 16);
+        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = silu_f(acc[c + i] * al[i] + be[i]);
+        sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                                   pack_bf16x2(r[6], r[7])));
+      }
+    }
+    if (tmem_empty) {   // this warp's accumulator columns are in shared memory: the MMA warp may overwrite them
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+    }
+    bar_epilogue_p(bar_id);   // both halves of every row are staged
+
+    // ---- phase 2: coalesced write-out of this warp's 16 rows
+#pragma unroll
+    for (int it = 0; it < O::NIT; ++it) {
+      const int row = row0 + it * O::RPI + sub_row;
+      const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, row);
+      if constexpr (KIND == G_RESID) {
+        float sq = 0.f;
+        if (ri.valid) {
+          char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
+          const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
+          float4 o = rres[it];
+          o.x += d.x;
+          o.y += d.y;
+          o.z += d.z;
+          o.w += d.w;
+          *reinterpret_cast<float4*>(dst) = o;
+          if (a.rb_out) {
+            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
+                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+          }
+        }
+        if (a.rb_out) {   // warp-uniform: reduce the row's LPR lanes, lane 0 of each row group stores the tile's sum
+#pragma unroll
+          for (int off = O::LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+          if (ri.valid && (lane % O::LPR) == 0) a.ss_out[ri.out_row * a.ss_ld + ty] = sq;
+        }
+      } else if (ri.valid) {
+        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
+        *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 template <int KIND, int BN, bool DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -704,6 +1146,283 @@ __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(con
   PROF_END();
 }
 
+
+// ---------------------------------------------------------------------------------------------- persistent kernel
+// Large-batch form of the dense kinds (thousands of rows).  At that size the GEMMs of this model are bound by the
+// L2 -> SM operand traffic (~6300 B/clk for the whole chip, ~80 GB/s per SM when all 148 pull at once), not by the
+// tensor pipe: a 128 x 128 x 64 step needs 32 KB of operands for 2.1 MFLOP.  Three things raise the FLOP per L2 byte
+// and hide the rest:
+//  * NSUB = 2: the tile is two adjacent 128-column weight tiles wide (MMA N = 256), so one A tile feeds twice the math;
+//  * PAIR: a 2-CTA cluster (cta_group::2, MMA M = 256) in which each CTA loads its own 128 rows of A and only ONE of
+//    the two 128-row weight tiles; the tensor cores of both SMs read both halves (131 FLOP per L2 byte instead of 64);
+//  * persistent CTAs (one per SM) walking tiles t = first, + stride, ... with the N tile fastest; the operand ring runs
+//    across tile boundaries and the accumulator is double buffered in TMEM, so the TMA warp prefetches and the MMA warp
+//    computes tile i + 1 while the eight epilogue warps drain tile i.
+// The epilogue code is the one-tile kernel's, called once per 128-column sub-tile.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void pair_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-CTA forms: the load lands in this CTA's shared memory and completes bytes on the LEADER's barrier; the MMA is
+// issued by the leader for both CTAs; the commit arrives on the barrier at the same offset in every CTA of the mask.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int KIND, int NSUB, bool PAIR>
+struct PersistCfg {
+  static constexpr int BN = 128;                                      // sub-tile width (the epilogue's tile)
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_ROWS = PAIR ? (NSUB * BN) / 2 : NSUB * BN;   // weight rows this CTA loads per K step
+  static constexpr int B_BYTES = B_ROWS * 128;
+  static constexpr int STAGE_BYTES = ((128 * OutCfg<KIND, BN>::STRIDE + 1023) / 1024) * 1024;   // epilogue staging
+  // Epilogue groups of 8 warps; group g drains accumulator buffer g.  One sub-tile epilogue is a chain of latencies
+  // (TMEM load, activation math, staging, barrier, stores: ~2 us), longer than the sub-tile's MMAs, so two of them run
+  // interleaved where the staging area is small enough to have two.
+  static constexpr int NGRP = STAGE_BYTES <= 20 * 1024 ? 2 : 1;
+  static constexpr int THREADS = 64 + NGRP * EPI_THREADS;
+  static constexpr int STAGES = (196 * 1024 - NGRP * STAGE_BYTES) / (A_BYTES + B_BYTES);
+  static constexpr int ACC_COLS = NSUB * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NGRP * STAGE_BYTES + 512 + NGRP * 1024 + 1024;
+  static_assert(NSUB == 1 || NSUB == 2, "one or two weight tiles per tile");
+  static_assert(!PAIR || NSUB == 2, "the pair form loads one 128-row weight tile per CTA");
+  static_assert(STAGES >= 3, "tile does not fit");
+};
+
+// grid: a multiple of the cluster size; unit = CTA (or CTA pair); tiles_y counts NSUB-wide column tiles; units walk
+// ntiles = (row tiles or row-tile pairs) x tiles_y.
+template <int KIND, int NSUB, bool PAIR>
+__global__ void __launch_bounds__(PersistCfg<KIND, NSUB, PAIR>::THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                          const __grid_constant__ CUtensorMap tmB,
+                                                                          const GemmArgs a, int tiles_y, int ntiles) {
+  static_assert(!KindTraits<KIND>::stream_rows && KIND != G_DECODER, "dense kinds only");
+  using Cfg = PersistCfg<KIND, NSUB, PAIR>;
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  char* stage = reinterpret_cast<char*>(sB + STAGES * Cfg::B_BYTES);            // [NGRP][STAGE_BYTES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage + Cfg::NGRP * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_cbase = reinterpret_cast<float*>(stage + Cfg::NGRP * Cfg::STAGE_BYTES + 512);   // [NGRP][256]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int nunits = PAIR ? gridDim.x >> 1 : gridDim.x;
+
+  PROF_DECL();
+  PROF_BEGIN(1000 + 100 * KIND + BN / 8);
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], PAIR ? 16 : 8);   // one arrive per epilogue warp (of both CTAs)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
+  }
+  tc_fence_before();
+  if constexpr (PAIR) pair_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) PROF_MARK(1);
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs of a pair): warp-uniform loop, one elected lane issues; the ring does
+    // not drain between tiles
+    int cnt = 0;
+    bool waited = false;
+    for (int t = unit; t < ntiles; t += nunits) {
+      const int tu = t / tiles_y, ty = t - tu * tiles_y;
+      const int tx = PAIR ? 2 * tu + (int)rank : tu;                               // this CTA's 128-row tile
+      for (int it = 0; it < a.nk; ++it, ++cnt) {
+        const int s = cnt % STAGES;
+        const uint32_t ph = (cnt / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if constexpr (PAIR) {
+          const uint32_t lbar = map_to_rank(smem_u32(&full[s]), 0);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(&full[s], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+            tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, lbar, it * 64, (ty * NSUB + (int)rank) * BN);
+          }
+          __syncwarp();
+          if (!waited) {   // activations come from the predecessor grid
+            pdl_wait();
+            waited = true;
+          }
+          if (elect_one_sync()) tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, lbar, it * 64, tx * 128);
+          __syncwarp();
+        } else {
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < NSUB; ++j)   // weights: no dependency
+              tma_load_2d(sB + s * Cfg::B_BYTES + j * BN * 128, &tmB, &full[s], it * 64, (ty * NSUB + j) * BN);
+          }
+          __syncwarp();
+          if (!waited) {
+            pdl_wait();
+            waited = true;
+            if (lane == 0) PROF_MARK(2);
+          }
+          if (elect_one_sync()) tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, &full[s], it * 64, tx * 128);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (the leader CTA of a pair)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(PAIR ? 256 : 128, NSUB * BN);
+      const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+      int cnt = 0, i = 0;
+      for (int t = unit; t < ntiles; t += nunits, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);   // the epilogue of tile i - 2 has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * Cfg::ACC_COLS;
+        for (int it = 0; it < a.nk; ++it, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          if (cnt == 0 && lane == 0) PROF_MARK(3);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(sA_u32 + s * Cfg::A_BYTES);
+          const uint64_t db = make_sw128_desc(sB_u32 + s * Cfg::B_BYTES);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (PAIR) umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (PAIR) umma_commit_pair(&empty[s]);
+            else umma_commit(&empty[s]);
+          }
+          __syncwarp();
+        }
+        if (elect_one_sync()) {
+          if constexpr (PAIR) umma_commit_pair(&tmem_full[buf]);
+          else umma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: group g = warps 2 + 8g .. 9 + 8g takes the tiles whose accumulator buffer is g
+    // (every tile when there is one group); one pass of the shared epilogue per 128-column sub-tile
+    const int g = (warp - 2) >> 3;
+    const int q = warp & 3, hf = ((warp - 2) >> 2) & 1;
+    const int et = (threadIdx.x - 64) & (EPI_THREADS - 1);
+    char* my_stage = stage + g * Cfg::STAGE_BYTES;
+    float* s_c0 = s_cbase + g * 256;
+    float* s_c1 = s_c0 + 128;
+    bool first = true;
+    int i = 0;
+    for (int t = unit; t < ntiles; t += nunits, ++i) {
+      const int buf = i & 1;
+      if (Cfg::NGRP == 2 && buf != g) continue;
+      const int tu = t / tiles_y, ty = t - tu * tiles_y;
+      const int tx = PAIR ? 2 * tu + (int)rank : tu;
+      const uint32_t empty_addr = PAIR ? map_to_rank(smem_u32(&tmem_empty[buf]), 0) : smem_u32(&tmem_empty[buf]);
+      if (first) pdl_wait();
+      first = false;
+      // row scale of the folded RMSNorm: one value per row, shared by the sub-tiles
+      float rs = 1.f;
+      if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
+        if (a.ss) {
+          const RowInfo rme = row_info_p<KIND, true>(a, tx, q * 32 + lane);
+          if (rme.valid) {
+            const float* sp = a.ss + rme.out_row * a.ss_ld;
+            float tsum = 0.f;
+            for (int k = 0; k < a.ss_tiles; ++k) tsum += sp[k];
+            rs = 1.0f / (sqrtf(tsum) * 0.05103103630798288f + 1e-8f);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        // every warp of the group is past phase 1 of the previous sub-tile (its mid barrier), so the constants may
+        // change; the barrier below also orders the previous phase-2 reads of the staging area before this phase 1
+        stage_constants_p<KIND, BN, true>(a, s_c0, s_c1, et, ty * NSUB + j);
+        bar_epilogue_p(1 + g);
+        epilogue_p<KIND, BN, true>(a, tmem_base + buf * Cfg::ACC_COLS + j * BN + (static_cast<uint32_t>(q * 32) << 16), q, hf, lane,
+                           my_stage, s_c0, s_c1, &tmem_full[buf], tx, ty * NSUB + j, (i >> 1) & 1,
+                           j == NSUB - 1 ? empty_addr : 0u, 1 + g, &rs);
+      }
+    }
+  }
+  tc_fence_before();
+  if constexpr (PAIR) pair_sync_all();
+  else __syncthreads();
+  if (warp == 1) {
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  PROF_END();
+}
+
 // Launch with (optional) programmatic stream serialization.
 template <typename Kern, typename... Args>
 inline cudaError_t launch_kernel(Kern kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
@@ -730,6 +1449,44 @@ inline cudaError_t configure_gemm_tc() {
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               TileCfg<BN, false>::SMEM_BYTES);
+}
+
+template <int KIND, int NSUB, bool PAIR>
+inline cudaError_t configure_gemm_tc_persist() {
+  return cudaFuncSetAttribute(gemm_tc_persist_kernel<KIND, NSUB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              PersistCfg<KIND, NSUB, PAIR>::SMEM_BYTES);
+}
+
+// m_tiles / n_tiles count 128 x 128 tiles; ctas = CTAs to launch at most (the SM count)
+template <int KIND, int NSUB, bool PAIR>
+inline cudaError_t launch_gemm_tc_persist(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a,
+                                          int m_tiles, int n_tiles, bool pdl, int ctas) {
+  const int tiles_y = n_tiles / NSUB;
+  const int ntiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * tiles_y;
+  int grid = PAIR ? 2 * std::min(ntiles, ctas / 2) : std::min(ntiles, ctas);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(PersistCfg<KIND, NSUB, PAIR>::THREADS);
+  cfg.dynamicSmemBytes = PersistCfg<KIND, NSUB, PAIR>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (PAIR) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_persist_kernel<KIND, NSUB, PAIR>, tmA, tmB, a, tiles_y, ntiles);
 }
 
 // deep = one CTA per SM, whole smem as the ring (grids that fit in one wave); otherwise two CTAs per SM.

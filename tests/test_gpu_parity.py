@@ -126,6 +126,40 @@ def test_step_matches_oracle(engines, weights, tb, C, B, n):
         eng.release_slots(slots)
 
 
+# ---- large-batch paths: 128-wide tiles (>= 2048 rows per lane), two concurrent lanes (>= 512 streams), and the
+# persistent GEMM kernel.  Streams are independent, so B streams that replay a handful of distinct signals must all
+# reproduce the oracle's answer for their signal (size-independent property; the oracle runs the distinct signals only).
+@pytest.mark.parametrize("C,B,persist,mode", [(2400, 600, None, None), (2400, 600, "0", "0"), (2400, 600, "1", "0"), (2400, 600, "1", "1"),
+                                               (2400, 600, "1", "2"), (3200, 420, "1", "2"), (2400, 230, "1", "2"),
+                                               (2400, 333, "1", "1")])
+def test_large_batch_paths_match_oracle(weights, tb, monkeypatch, C, B, persist, mode):
+    # persist: smallest GEMM (in 128 x 128 tiles) that takes the persistent kernel, 0 = never; mode: its tile form
+    # (0 = 128 wide, 1 = 256 wide, 2 = 256 wide on CTA pairs)
+    if persist is not None:   # None = the engine's defaults
+        monkeypatch.setenv("TONE_PERSIST_MIN_TILES", persist)
+        monkeypatch.setenv("TONE_PERSIST_MODE", mode)
+    n, D = 3, 6
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B)
+    try:
+        W = orc.to_torch(weights)
+        distinct = tb.synth.telephony_pcm(D, C * n, seed=77)
+        idx = np.arange(B) % D
+        pcm = np.ascontiguousarray(distinct[idx])
+        slots = eng.alloc_slots(B)
+        lp, tk = _stream_engine(eng, slots, pcm, C)
+        ref, st = _stream_oracle(W, distinct, C)
+        assert np.isfinite(lp).all()
+        assert np.abs(lp - ref[:, idx]).max() <= LP_TOL
+        assert (tk == lp.argmax(-1)).all()
+        _check_tokens(tk, ref[:, idx])
+        flat_ref = orc.pack_state(st).astype(np.float32)
+        for b in (0, 1, B // 2, B - 2, B - 1):
+            got = eng.export_state(int(slots[b])).astype(np.float32)
+            assert np.abs(got - flat_ref[idx[b]]).max() <= ST_TOL
+    finally:
+        eng.close()
+
+
 # ---- experimental cluster (latency) path: the 16 layers + decoder as one thread-block-cluster kernel
 @pytest.mark.parametrize("C,B,n,G", [(2400, 5, 5, None), (3200, 7, 4, None), (2400, 64, 3, None), (2400, 66, 2, "4"),
                                      (2400, 78, 2, "5"), (3200, 50, 2, "3")])
