@@ -579,32 +579,6 @@ __device__ __forceinline__ RowInfo row_info_p(const GemmArgs& a, int tx, int row
   return ri;
 }
 
-template <int KIND, int BN, bool PERSIST = true>
-__device__ __forceinline__ void stage_constants_p(const GemmArgs& a, float* s_c0, float* s_c1, int t /*0..255*/, int ty) {
-  const int n0 = ty * BN;
-  if constexpr (KIND == G_PARTIAL) {
-    return;
-  } else if constexpr (KIND == G_CONV0 || KIND == G_CONV1) {
-    constexpr int CH = (KIND == G_CONV0) ? 32 : 64;
-    if (t < BN) {
-      s_c0[t] = __ldg(a.alpha + (n0 + t) % CH);
-      s_c1[t] = __ldg(a.beta + (n0 + t) % CH);
-    }
-  } else if constexpr (KIND == G_DECODER) {
-    if (t < 48) s_c0[t] = t < 35 ? __ldg(a.bias + t) : 0.f;
-  } else if constexpr (KIND == G_GLU_DW) {
-    if (t < BN) s_c0[t] = __ldg(a.bias + n0 + t);
-    // depthwise taps [31][32] + bias [32] of this tile's 32 channels, behind the per-column constants
-    float* wS = s_c1 + 128;
-    for (int i = t; i < 32 * 32; i += EPI_THREADS) {
-      const int j = i >> 5, c = i & 31;
-      wS[i] = (j < 31) ? __ldg(a.dw_w + j * 384 + ty * 32 + c) : __ldg(a.dw_b + ty * 32 + c);
-    }
-  } else {
-    if (t < BN) s_c0[t] = a.bias ? __ldg(a.bias + n0 + t) : 0.f;
-  }
-}
-
 // Named barrier of one epilogue group (ids 1 and 2).
 __device__ __forceinline__ void bar_epilogue_p(int id = 1) {   // immediate barrier ids (the id is a constant after inlining)
   if (id == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1385,6 +1359,12 @@ __global__ void __launch_bounds__(PersistCfg<KIND, NSUB, PAIR>::THREADS, 1) gemm
       const int tu = t / tiles_y, ty = t - tu * tiles_y;
       const int tx = PAIR ? 2 * tu + (int)rank : tu;
       const uint32_t empty_addr = PAIR ? map_to_rank(smem_u32(&tmem_empty[buf]), 0) : smem_u32(&tmem_empty[buf]);
+      // per-column constants (bias) of both sub-tiles: weights, loaded here so that their L2 round trip overlaps the
+      // row-scale loads and the wait for the accumulator instead of sitting in front of every sub-tile
+      float cpre[NSUB];
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j)
+        cpre[j] = (KIND != G_PARTIAL && et < BN && a.bias) ? __ldg(a.bias + (ty * NSUB + j) * BN + et) : 0.f;
       if (first) pdl_wait();
       first = false;
       // row scale of the folded RMSNorm: one value per row, shared by the sub-tiles
@@ -1404,7 +1384,7 @@ __global__ void __launch_bounds__(PersistCfg<KIND, NSUB, PAIR>::THREADS, 1) gemm
       for (int j = 0; j < NSUB; ++j) {
         // every warp of the group is past phase 1 of the previous sub-tile (its mid barrier), so the constants may
         // change; the barrier below also orders the previous phase-2 reads of the staging area before this phase 1
-        stage_constants_p<KIND, BN, true>(a, s_c0, s_c1, et, ty * NSUB + j);
+        if (KIND != G_PARTIAL && et < BN) s_c0[et] = cpre[j];
         bar_epilogue_p(1 + g);
         epilogue_p<KIND, BN, true>(a, tmem_base + buf * Cfg::ACC_COLS + j * BN + (static_cast<uint32_t>(q * 32) << 16), q, hf, lane,
                            my_stage, s_c0, s_c1, &tmem_full[buf], tx, ty * NSUB + j, (i >> 1) & 1,
