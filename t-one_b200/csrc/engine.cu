@@ -1406,7 +1406,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.bias = L.dw_b;
       d.e = ln.ebuf;
       d.T = Tl;
-      KLAUNCH(launch_kernel(dwconv_kernel, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
+      const int dw_half = (Tl + 1) / 2;   // output frames per thread
+      if (dw_half <= 3) KLAUNCH(launch_kernel(dwconv_kernel<3>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
+      else if (dw_half <= 5) KLAUNCH(launch_kernel(dwconv_kernel<5>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
+      else KLAUNCH(launch_kernel(dwconv_kernel<DW_TH>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
     }
     RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles));
     // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer

@@ -686,6 +686,9 @@ constexpr int DW_ROWS = CONV_S + MAX_T;          // 43
 constexpr int DW_RV = DW_CH / 8;                 // uint4 per tile row
 constexpr int DW_TH = (MAX_T + 1) / 2;           // output frames per thread (7)
 
+// TH = output frames per thread = ceil(T / 2), a template parameter so that the unrolled tap loop does no work for frames
+// that do not exist (T = 10 -> 5, T = 13 -> 7, reduced-rate layers T = 5 / 6 -> 3): the kernel is bound by FMA issue.
+template <int TH>
 __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
   __shared__ __align__(16) bf16 tile[DW_ROWS][DW_CH];
   PROF_DECL();
@@ -728,22 +731,22 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
   // this thread's frames: t0 .. t0 + DW_TH - 1 (clipped to T)
   const int half = (T + 1) / 2;
   const int t0 = th * half;
-  float acc[DW_TH];
+  float acc[TH];
 #pragma unroll
-  for (int t = 0; t < DW_TH; ++t) acc[t] = bb;
+  for (int t = 0; t < TH; ++t) acc[t] = bb;
 #pragma unroll
-  for (int i = 0; i < CONV_S + DW_TH; ++i) {             // rows t0 + i of the tile
+  for (int i = 0; i < CONV_S + TH; ++i) {             // rows t0 + i of the tile
     if (t0 + i < CONV_S + T) {
       const float x = __bfloat162float(tile[t0 + i][cl]);
 #pragma unroll
-      for (int t = 0; t < DW_TH; ++t) {
+      for (int t = 0; t < TH; ++t) {
         const int j = i - t;                               // compile-time after unrolling
         if (j >= 0 && j <= CONV_S) acc[t] = fmaf(w[j], x, acc[t]);
       }
     }
   }
 #pragma unroll
-  for (int t = 0; t < DW_TH; ++t)
+  for (int t = 0; t < TH; ++t)
     if (t < half && t0 + t < T) a.e[(size_t)(b * T + t0 + t) * D_MODEL + c] = __float2bfloat16(silu_f(acc[t]));
   // new cache = last 30 rows of [cache | g]
   {
