@@ -8,8 +8,20 @@
  *
  * Conventions: every function returns 0 on success or a negative TONE_E* code and never
  * throws across the ABI; tone_last_error() returns a thread-local description of the last
- * failure.  A handle is not thread-safe: one stepping thread per engine (the reference is a
- * synchronous call as well, tone/onnx_wrapper.py:84-123).  Plain pointers and sizes only.
+ * failure.  Plain pointers and sizes only.
+ *
+ * Threading and stream ordering.  A handle is not thread-safe: one stepping thread per engine
+ * (the reference is a synchronous call as well, tone/onnx_wrapper.py:84-123).  All work of an
+ * engine is ordered on its own streams; the engine records an event after every launch, and
+ * every entry point that reads results (tone_fetch*, tone_wait, tone_export_*) or overwrites
+ * inputs waits on the events it depends on.  Entry points that take a caller `cuda_stream` make
+ * that stream wait for the engine's pending input copies and previous step before launching, and
+ * the engine's later work waits for that launch; the caller only has to keep its own buffers
+ * alive and unchanged until the work it enqueued on its stream has completed.
+ *
+ * Slot ids within one batch must be distinct (two entries of one stream in one step would be a
+ * data race on that stream's caches): every entry point validates range, allocation and
+ * uniqueness on the host and returns TONE_EINVAL / TONE_ESTATE.
  */
 #ifndef TONE_B200_H
 #define TONE_B200_H
@@ -21,31 +33,57 @@ extern "C" {
 #endif
 
 #define TONE_OK 0
-#define TONE_EINVAL (-1)   /* bad argument (shape / range / null)              -> ValueError */
-#define TONE_ENOMEM (-2)   /* out of slots or device memory                                  */
-#define TONE_ECUDA (-3)    /* CUDA runtime / driver failure, see tone_last_error()           */
-#define TONE_ESTATE (-4)   /* call order: weights not finalized, slot not allocated, ...     */
-#define TONE_ERANGE (-5)   /* PCM sample outside [-32768, 32767] (tone/onnx_wrapper.py:108)  */
+#define TONE_EINVAL (-1)   /* bad argument (shape / null / duplicate slot)         -> ValueError */
+#define TONE_ENOMEM (-2)   /* out of slots or device memory                                      */
+#define TONE_ECUDA (-3)    /* CUDA runtime / driver failure, see tone_last_error()               */
+#define TONE_ESTATE (-4)   /* call order: weights not finalized, slot not allocated, ticket ...  */
+#define TONE_ERANGE (-5)   /* PCM sample outside [-32768, 32767] (tone/onnx_wrapper.py:108-113)  */
 
 #define TONE_STATE_SIZE 219729 /* fp16 elements per stream, tone/onnx_wrapper.py:34 */
 #define TONE_N_CLASSES 35      /* 34 labels + CTC blank, tone/decoder.py:23         */
 
+/* PCM sample formats accepted on the wire.  The reference's "signal" tensor is int32 holding int16-range
+ * values (configs/streaming_acoustic/config.pbtxt:5-11, tone/onnx_wrapper.py:104-113); telephony audio is
+ * int16 natively, so the int16 form halves the H2D bytes and cannot be out of range. */
+#define TONE_PCM_I32 0
+#define TONE_PCM_I16 1
+
+/* What a step leaves for the host (bit mask, `outputs` argument of tone_submit):
+ *   LOGPROBS  fp32 [B][T][35]                        ("logprobs", tone/onnx_wrapper.py:123)
+ *   TOKENS    int32 [B][T] per-frame argmax          (tone/decoder.py:57)
+ *   SIL       fp32 [B][T][2] log-probs of ' ' / blank (what tone/logprob_splitter.py:129 thresholds on)
+ *   PHRASES   finished phrases of the device-side splitter + greedy decoder (tone_phrase records) */
+#define TONE_OUT_LOGPROBS 1
+#define TONE_OUT_TOKENS 2
+#define TONE_OUT_SIL 4
+#define TONE_OUT_PHRASES 8
+
 typedef struct tone_engine tone_engine;
 
 /* Replaces the choice of exported model + session options
- * (tone/onnx_wrapper.py:66-78, configs/streaming_acoustic/config.pbtxt:1-44). */
+ * (tone/onnx_wrapper.py:66-78, configs/streaming_acoustic/config.pbtxt:1-44).
+ * Tuning fields: 0 selects the engine default everywhere. */
 typedef struct tone_config {
   int32_t device;        /* CUDA ordinal                                                    */
   int32_t chunk_samples; /* 2400 (300 ms, tone/onnx_wrapper.py:32) or 3200 (400 ms variant,  */
                          /* dev/triton/client_wer.py:277-278)                                */
   int32_t max_slots;     /* resident streams (state pool capacity)                           */
-  int32_t max_batch;     /* largest B accepted by tone_step                                  */
+  int32_t max_batch;     /* largest B accepted by a step                                     */
   int32_t gemm_impl;     /* 0 = tcgen05/TMEM/TMA (product path), 1 = SIMT debug kernels      */
   int32_t use_graph;     /* 1 = replay a captured CUDA graph per batch size, 0 = eager       */
-  int32_t cluster_max_batch; /* experimental latency path: batches up to this size run the 16  */
-                         /* Conformer layers + decoder as ONE thread-block-cluster kernel     */
-                         /* (csrc/encoder_cluster.cuh); 0 = off (default)                    */
+  /* ---- tuning (0 = default) */
+  int32_t lanes;             /* concurrent sub-batches a large step is cut into (1..4; default 2)           */
+  int32_t lane_min_batch;    /* streams per lane below which the batch is not cut (default 256)              */
+  int32_t persist_min_tiles; /* dense GEMMs with at least this many 128x128 tiles run as the persistent      */
+                             /* kernel (default: SM count + 1; -1 = never)                                   */
+  int32_t persist_mode;      /* gated persistent GEMMs: 1 = 128-wide tiles, 2 = 256-wide (default),          */
+                             /* 3 = 256-wide on CTA pairs (cta_group::2)                                     */
+  int32_t split_k;           /* split-K factor of the feed-forward down projection (default: fill the SMs)   */
+  int32_t flags;             /* TONE_FLAG_* bits                                                             */
 } tone_config;
+
+#define TONE_FLAG_NO_PDL 1         /* launch the kernels of a step without programmatic dependent launch     */
+#define TONE_FLAG_NO_FUSED_VATT 2  /* score-sharing layers: V projection and P.V as two kernels              */
 
 /* Shapes a caller needs to size its buffers (tone/onnx_wrapper.py:30-34,
  * configs/streaming_acoustic/config.pbtxt:5-33). */
@@ -55,10 +93,12 @@ typedef struct tone_info {
   int32_t n_classes;        /* 35                                            */
   int32_t state_size;       /* 219729                                        */
   int32_t max_slots, max_batch;
-  int32_t launches_per_step; /* kernels launched by one step (filled after the first step) */
+  int32_t launches_per_step; /* kernels launched by the last enqueued step                   */
   int32_t n_taps;            /* rows of the debug tap buffer: 1 + n_layers   */
   int64_t state_bytes_per_slot;
   int64_t weight_bytes;
+  int32_t pipeline_depth;    /* staging sets of tone_submit / tone_wait (2)  */
+  int32_t max_phrases_per_step; /* capacity of the phrase records of one step: 4 * max_batch */
 } tone_info;
 
 int tone_create(const tone_config* cfg, tone_engine** out);
@@ -66,7 +106,7 @@ void tone_destroy(tone_engine* e);
 int tone_get_info(const tone_engine* e, tone_info* out);
 const char* tone_last_error(void);
 
-/* Weights: one call per tensor with the reference state_dict name (without the `tone.`
+/* Weights: one call per tensor with the reference state_dict name (with or without the `tone.`
  * prefix; tone/training/model_wrapper.py:146,156) and fp32 data in the reference's shape.
  * Replaces ort.InferenceSession(model_path) (tone/onnx_wrapper.py:77).  tone_finalize_weights
  * folds/permutes/rounds them into the device layouts and uploads. */
@@ -75,19 +115,56 @@ int tone_finalize_weights(tone_engine* e);
 
 /* Stream slots: server-resident per-stream state, the role of Triton's implicit sequence
  * state (triton/model/config.pbtxt:26-69).  A fresh slot holds the all-zero initial state
- * (tone/nn/model.py:208-267, tone/onnx_wrapper.py:114-115). */
+ * (tone/nn/model.py:208-267, tone/onnx_wrapper.py:114-115) and an empty phrase-splitter state
+ * (tone/logprob_splitter.py:33-38). */
 int tone_alloc_slots(tone_engine* e, int32_t n, int32_t* slots_out);
 int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slots);
 int tone_reset_slots(tone_engine* e, int32_t n, const int32_t* slots);
 
 /* The step: replaces `_ort_sess.run(None, {"signal","state"})` (tone/onnx_wrapper.py:123).
- *   pcm       host int32 [B][chunk_samples]   ("signal", int16 range)
+ *   pcm       host int32 [B][chunk_samples]   ("signal"); a sample outside the int16 range -> TONE_ERANGE
  *   logprobs  host fp32  [B][frames_out][35]  ("logprobs"), may be NULL
  *   tokens    host int32 [B][frames_out]      per-frame argmax (first max, tone/decoder.py:57), may be NULL
  * State is read from and written back to slots[b] on the device.  Synchronous: returns when
  * the outputs are in the host buffers.  H2D of pcm and D2H of the outputs are part of the call. */
 int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm,
               float* logprobs, int32_t* tokens);
+
+/* Pipelined form of the step for serving loops: tone_submit enqueues (H2D on a copy stream -> step -> D2H on a
+ * second copy stream) on one of `pipeline_depth` staging sets and returns a ticket immediately; tone_wait blocks
+ * until that ticket's outputs are on the host.  With two tickets in flight the copies of step i+1 / i-1 overlap
+ * the kernels of step i.  Steps execute in submission order (a stream may appear in consecutive tickets).
+ *   pcm         host [B][chunk_samples] int32 or int16 (pcm_format); int32 is range-checked (TONE_ERANGE)
+ *   is_last     host uint8 [B] or NULL: 1 = this is the stream's last chunk, flush its unfinished phrase
+ *               (`is_last` of tone/logprob_splitter.py:91-97 / tone/pipeline.py:200); only used with PHRASES
+ *   outputs     TONE_OUT_* mask: only these are produced / copied back
+ * tone_wait copies into the caller's buffers (each nullable; must have been requested): logprobs [B][T][35],
+ * tokens [B][T], sil [B][T][2]; phrases are read with tone_ticket_phrases until the set is reused by a later
+ * submit.  A set must be waited on before it is submitted again (TONE_ESTATE otherwise). */
+int tone_submit(tone_engine* e, int32_t B, const int32_t* slots, const void* pcm, int32_t pcm_format,
+                const uint8_t* is_last, int32_t outputs, int32_t* ticket_out);
+int tone_wait(tone_engine* e, int32_t ticket, float* logprobs, int32_t* tokens, float* sil);
+
+/* Pinned staging of the set the NEXT tone_submit will use: writing the inputs there (and passing these very
+ * pointers to tone_submit with TONE_PCM_I16) skips the intermediate host copy.  PCM always crosses PCIe as int16
+ * (int32 input is range-checked and narrowed while it is copied into this staging). */
+int tone_next_staging(tone_engine* e, int32_t** slots, int16_t** pcm16, uint8_t** is_last);
+
+/* Device-side phrase splitter + greedy CTC decoder (tone/logprob_splitter.py:60-153, tone/decoder.py:57-59,
+ * the frame arithmetic of tone/pipeline.py:149-171 stays with the caller).  One record per finished phrase:
+ * the frame interval [start_frame, end_frame) in the stream's own frame count, and the greedy text as label ids
+ * (argmax -> repeats collapsed -> blank dropped -> leading/trailing ' ' stripped; ids index tone/decoder.py:23). */
+typedef struct tone_phrase {
+  int32_t batch_index;   /* position of the stream in the submitted batch                         */
+  int32_t start_frame;   /* LogprobPhrase.start_frame (tone/logprob_splitter.py:139)              */
+  int32_t end_frame;     /* LogprobPhrase.end_frame                                               */
+  int32_t text_offset;   /* first label id of this phrase in the ticket's text pool               */
+  int32_t text_len;      /* number of label ids                                                   */
+} tone_phrase;
+/* After tone_wait(ticket): the ticket's phrase records (in (batch_index, time) order per stream; streams in
+ * arbitrary order) and its text pool; the pointers stay valid until the staging set is submitted again. */
+int tone_ticket_phrases(tone_engine* e, int32_t ticket, const tone_phrase** phrases, int32_t* n_phrases,
+                        const uint8_t** text_pool, int32_t* text_pool_len);
 
 /* Feature-input form of the step: replaces the exported graph built with `--skip-preprocessor`
  * (tone/nn/model.py:151-160, tone/scripts/export.py:48-49), i.e. the acoustic model behind an external log-mel front
@@ -98,14 +175,14 @@ int tone_step_features(tone_engine* e, int32_t B, const int32_t* slots, const ui
                        float* logprobs, int32_t* tokens);
 
 /* Same step with inputs/outputs left in HBM: stage once, then step any number of times on
- * the staged chunk (benchmark "inputs already resident" leg).  tone_fetch copies the last
- * outputs to the host. */
+ * the staged chunk.  tone_fetch / tone_fetch_greedy copy the last step's outputs to the host (they wait for
+ * the last launch, whichever stream it went to). */
 int tone_stage(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm);
 int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream);
 int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens);
 int tone_sync(tone_engine* e);
 
-/* Greedy fast path (SURVEY 8f-2): instead of the full log-probs, fetch per frame the argmax token and the two
+/* Greedy fast path: instead of the full log-probs, fetch per frame the argmax token and the two
  * log-probs the phrase splitter thresholds on - ' ' (id 33) and blank (id 34), tone/logprob_splitter.py:129.
  *   tokens        host int32 [B][frames_out]
  *   sil_logprobs  host fp32  [B][frames_out][2]
@@ -113,22 +190,27 @@ int tone_sync(tone_engine* e);
 int tone_fetch_greedy(tone_engine* e, int32_t B, int32_t* tokens, float* sil_logprobs);
 
 /* Device-pointer form of the step for GPU-resident producers/consumers (the role of Triton's
- * GPU tensors between ensemble stages, triton/ensemble/config.pbtxt:20-55): slots / pcm are
- * device int32 buffers, logprobs / tokens device outputs (any may be NULL = use what is staged /
- * leave in the engine).  Enqueued on `cuda_stream` (NULL = the engine's stream); asynchronous. */
-int tone_step_device(tone_engine* e, int32_t B, const int32_t* d_slots, const int32_t* d_pcm,
+ * GPU tensors between ensemble stages, triton/ensemble/config.pbtxt:20-55).
+ *   slots       HOST int32 [B] (validated like tone_step; copied to the device by the call)
+ *   d_pcm       device [B][chunk_samples] in pcm_format; NULL = step again on what is staged
+ *   d_logprobs  device fp32 [B][T][35] or NULL;  d_tokens device int32 [B][T] or NULL
+ * Enqueued on `cuda_stream` (NULL = the engine's stream); asynchronous; see the ordering contract above. */
+int tone_step_device(tone_engine* e, int32_t B, const int32_t* slots, const void* d_pcm, int32_t pcm_format,
                      float* d_logprobs, int32_t* d_tokens, void* cuda_stream);
 
-/* Pinned host staging buffers owned by the engine (slots [max_batch], pcm [max_batch][chunk],
- * logprobs [max_batch][T][35], tokens [max_batch][T]).  Passing these pointers to tone_step /
- * tone_stage / tone_fetch skips the intermediate host copy. */
-int tone_host_buffers(tone_engine* e, int32_t** slots, int32_t** pcm, float** logprobs, int32_t** tokens);
-
-/* State wire format: the reference's flat fp16 vector ("state"/"state_next",
- * configs/streaming_acoustic/config.pbtxt:12-33; element order = get_initial_state order,
- * tone/nn/model.py:259-267).  Used for parity, checkpoint/resume and stream migration. */
-int tone_export_state(tone_engine* e, int32_t slot, uint16_t* fp16_out /* [219729] */);
-int tone_import_state(tone_engine* e, int32_t slot, const uint16_t* fp16_in /* [219729] */);
+/* State wire formats.  Used for parity, checkpoint/resume and stream migration; batched (n slots per call,
+ * one device gather/scatter kernel and one copy).
+ * Flat: the reference's fp16 vector ("state"/"state_next", configs/streaming_acoustic/config.pbtxt:12-33;
+ * element order = get_initial_state order, tone/nn/model.py:259-267). */
+int tone_export_states(tone_engine* e, int32_t n, const int32_t* slots, uint16_t* fp16_out /* [n][219729] */);
+int tone_import_states(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* fp16_in /* [n][219729] */);
+/* Three-tensor Triton cache layout of the newer export (tone/scripts/export.py:293-376,
+ * triton/model/config.pbtxt:44-66): cache_last_time fp16 [n][18][384][30], cache_last_channel fp16 [n][32][8][50],
+ * cache_last_chan_len int64 [n]. */
+int tone_export_states_triton(tone_engine* e, int32_t n, const int32_t* slots, uint16_t* cache_last_time,
+                              uint16_t* cache_last_channel, int64_t* cache_last_chan_len);
+int tone_import_states_triton(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* cache_last_time,
+                              const uint16_t* cache_last_channel, const int64_t* cache_last_chan_len);
 
 /* Debug: run one eager step that also records the residual stream after pre-encode and after
  * every Conformer layer.  taps: host fp32 [1+n_layers][B*frames_out][384] (rows of reduced
@@ -141,10 +223,12 @@ int tone_step_debug(tone_engine* e, int32_t B, const int32_t* slots, const int32
 int tone_selftest_gemm(tone_engine* e, int32_t M, int32_t N, int32_t K, const float* A, const float* W,
                        float* C, int32_t block_n);
 
-/* Debug: diagnostics of the experimental cluster (latency) path.  out (nullable): 6144 uint64 of in-kernel
- * timestamps of the last cluster-kernel launch (needs TONE_CL_PROF=1 at tone_create); max_active (nullable):
- * co-resident clusters reported by the occupancy query, small-group * 1000 + large-group instantiation. */
-int tone_cluster_prof_read(tone_engine* e, unsigned long long* out, int32_t* max_active);
+/* Debug: run the device-side phrase splitter + greedy decoder alone on host-supplied per-frame inputs (one stream
+ * per slot, `frames` frames each): tokens int32 [B][frames], sil fp32 [B][frames][2].  Lets the splitter be
+ * checked against the reference's StreamingLogprobSplitter + GreedyCTCDecoder on arbitrary log-prob streams.
+ * Results are read with tone_ticket_phrases(e, -1, ...). */
+int tone_selftest_phrases(tone_engine* e, int32_t B, const int32_t* slots, int32_t frames, const int32_t* tokens,
+                          const float* sil, const uint8_t* is_last);
 
 #ifdef __cplusplus
 }

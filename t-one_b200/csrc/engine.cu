@@ -29,7 +29,8 @@
 #include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
-#include "encoder_cluster.cuh"
+#include "ctc_phrase.cuh"
+#include "state_io.cuh"
 
 using namespace tone;
 
@@ -48,6 +49,12 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(TONE_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
   } while (0)
 
+#define RC(x)              \
+  do {                     \
+    int _rc = (x);         \
+    if (_rc) return _rc;   \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------ host bf16/fp16
 static inline uint16_t f2bf(float f) {
   uint32_t u;
@@ -56,7 +63,7 @@ static inline uint16_t f2bf(float f) {
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-static inline float bf2f(uint16_t h) {
+[[maybe_unused]] static inline float bf2f(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
   memcpy(&f, &u, 4);
@@ -91,8 +98,8 @@ struct WeightMat {      // a bf16 [N][K] matrix on the device with its TMA map (
 };
 
 struct LayerW {
-  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw1w, pw1c, pw2;   // pw1w: pw1 packed for 128-wide tiles
-  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw1w_b, *pw1c_b, *pw2_b;   // pw1c: per-CTA [a 48 | b 48] blocks (cluster path)
+  WeightMat ff1_up, ff1_down, ff2_up, ff2_down, qkv, q, kv, wo, pw1, pw1w, pw2;   // pw1w: pw1 packed for 128-wide tiles
+  float *ff1_up_b, *ff1_down_b, *ff2_up_b, *ff2_down_b, *qkv_b, *q_b, *kv_b, *wo_b, *pw1_b, *pw1w_b, *pw2_b;
   float *n_ff1, *n_att, *n_conv, *n_ff2, *n_out;
   float *qln_w, *qln_b, *kln_w, *kln_b;
   float *dw_w, *dw_b;
@@ -131,16 +138,50 @@ struct tone_engine {
   bf16 *st_feat, *st_x1, *st_kv14, *st_kv15, *st_conv;
   float* st_red;
   int* st_len;
+
+  // phrase splitter state (ctc_phrase.cuh)
+  PhSlot* st_ph = nullptr;
+  unsigned char* st_ring = nullptr;
   std::vector<int> free_slots;
   std::vector<char> slot_used;
+  std::vector<uint32_t> slot_stamp;     // duplicate detection: stamp of the last batch that named the slot
+  uint32_t stamp_gen = 0;
 
-  // step inputs / outputs (batch order)
-  int rows_alloc;
-  int *d_slots, *d_pcm, *d_len_in, *d_tokens;
-  __half* d_feats;   // [max_batch][64][MAX_FRAMES] feature-input mode staging
-  uint16_t* p_feats; // pinned
-  float* logprobs;
-  float* d_aux;      // [rows][2] logprob of space / blank per frame (greedy fast path)
+  // Step inputs / outputs, per staging set.  Sets 0 .. PIPE-1 form the ring of tone_submit / tone_wait (PCM int16);
+  // set PIPE serves the staged / device-pointer / feature / debug entry points (PCM int16 or int32).
+  struct IoSet {
+    int *d_slots = nullptr, *d_tokens = nullptr, *d_len_in = nullptr;
+    void* d_pcm = nullptr;
+    unsigned char* d_last = nullptr;
+    float *d_logprobs = nullptr, *d_aux = nullptr;
+    char* d_ph = nullptr;                 // PhHeader | PhRecord[4 B] | text pool
+    int* p_slots = nullptr;
+    int16_t* p_pcm = nullptr;
+    unsigned char* p_last = nullptr;
+    float *p_logprobs = nullptr, *p_aux = nullptr;
+    int* p_tokens = nullptr;
+    char* p_ph = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_step = nullptr, ev_out = nullptr;
+    bool busy = false;
+    int B = 0, outputs = 0, ticket = -1;
+    int staged_mode = 0;                  // legacy set: SM_PCM16 if the staged PCM is int16
+    bool ph_complete = true;              // the whole text pool of the ticket is on the host
+  };
+  static const int PIPE = 2;
+  IoSet io[PIPE + 1];
+  int next_ticket = 0;
+  size_t ph_bytes = 0;                    // bytes of one set's phrase area
+  __half* d_feats = nullptr;   // [max_batch][64][MAX_FRAMES] feature-input mode staging
+  uint16_t* p_feats = nullptr; // pinned
+  // small pinned ring for the slot ids of the asynchronous entry points (reset, device step, state io)
+  static const int RING = 8;
+  int* p_ring = nullptr;
+  int* d_ring = nullptr;
+  cudaEvent_t ev_ring[RING] = {};
+  int ring_pos = 0;
+  uint16_t* d_state_io = nullptr;         // [STATE_IO_CHUNK][219729] fp16 staging of the state wire format
+  uint16_t* p_state_io = nullptr;
+  int rows_alloc = 0;
   int max_splits = 8;
   CUtensorMap m_feat, m_x1, m_kv14, m_kv15;
   CUtensorMap w_feat, w_x1, w_kv14, w_kv15;   // same views with a box spanning the G slots of one tile
@@ -156,7 +197,8 @@ struct tone_engine {
     cudaEvent_t done = nullptr;
     // view of the sub-batch this lane is working on (set per step)
     const int* slots;
-    const int* pcm;
+    const void* pcm;
+    int pcm_fmt;
     const __half* feats;                 // non-null: feature-input mode
     int* len_in;
     float* lp_out;
@@ -166,37 +208,23 @@ struct tone_engine {
   std::vector<Lane> lanes;
   int n_lanes = 2, lane_min_batch = 256;   // measured: lanes only pay once kernels are throughput bound (B >= 512)
   cudaEvent_t fork_ev = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined step
+  cudaStream_t s_cap = nullptr;                   // graph capture happens on a stream of its own
+  cudaEvent_t ev_sync = nullptr, ev_last = nullptr;   // splice of caller-stream launches into the engine's timeline
 
-  // pinned staging
-  int *p_slots, *p_pcm, *p_tokens;
-  float *p_logprobs, *p_aux;
-
-  std::unordered_map<int, cudaGraphExec_t> graphs;
+  std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   int launches = 0, launches_per_step = 0;
-  bool pdl = true;      // programmatic dependent launch between the kernels of a step (TONE_PDL=0 disables)
-  // conv module's GLU GEMM + depthwise conv in one kernel (TONE_FUSE_DW=1).  Correct but measured SLOWER on B200
-  // (19.9 us vs 3.8 + 7.0 us): four epilogue warps per CTA cannot keep enough cache-column loads in flight.
-  bool fuse_dw = false;
+  bool pdl = true;      // programmatic dependent launch between the kernels of a step (TONE_FLAG_NO_PDL disables)
   // Large dense GEMMs (>= persist_min_tiles output tiles) run as a persistent one-CTA-per-SM kernel with the epilogue
   // overlapped with the next tile's main loop (gemm_tc_persist_kernel); 0 = never.
-  // (default: more tiles than SMs, set in tone_create).  TONE_PERSIST_MIN_TILES / TONE_PERSIST_MODE override.
   int persist_min_tiles = 0, persist_ctas = 0;
   // gated kinds (N % 256 == 0): 0 = 128-wide tiles, 1 = 256-wide, 2 = 256-wide on CTA pairs (cta_group::2).  Measured
   // (profiles/r01_persistent_gemm.md): the pair form runs the feed-forward up GEMM at 73 % of the sustained bf16 peak when
   // it has the GPU to itself, but with two lanes in flight the 256-wide single-CTA form gives the faster step.
   int persist_mode = 1;
-  bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel (TONE_FUSE_VATT=0: two kernels)
+  int split_k = 0;         // 0 = fill the SMs once
+  bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
   int num_sms = 148;
-
-  // latency path: the 16 layers + decoder as one thread-block-cluster kernel (encoder_cluster.cuh)
-  bool cluster_ok = false;        // built and launchable on this device
-  int cluster_max_batch = 0;      // batches up to this size take the cluster path (TONE_CLUSTER_MAX_B); 0 = off
-  int cluster_max_active[2] = {0, 0};   // co-resident clusters of the small-G / large-G instantiation (occupancy query)
-  int cluster_Gs[2] = {4, 5};           // streams per cluster: 4 | 5 at T = 10, 3 | 4 at T = 13
-  CUtensorMap* d_cl_maps = nullptr;
-  ClParams* d_clp = nullptr;
-  float* d_taps = nullptr;        // debug: [17][rows_alloc][384]
-  unsigned long long* d_cl_prof = nullptr;   // TONE_CL_PROF=1: in-kernel timeline of cluster 0 / CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -293,12 +321,17 @@ static const int BIG_M = 2048;
 
 extern "C" const char* tone_last_error(void) { return g_err; }
 
+static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceProp& prop);
+
 extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   if (!cfg || !out) return fail(TONE_EINVAL, "null argument");
   if (cfg->chunk_samples != 2400 && cfg->chunk_samples != 3200)
     return fail(TONE_EINVAL, "chunk_samples must be 2400 (300 ms) or 3200 (400 ms), got %d", cfg->chunk_samples);
   if (cfg->max_slots < 1 || cfg->max_batch < 1 || cfg->max_batch > cfg->max_slots)
     return fail(TONE_EINVAL, "need 1 <= max_batch <= max_slots");
+  if (cfg->lanes < 0 || cfg->lanes > 4 || cfg->persist_mode < 0 || cfg->persist_mode > 3 || cfg->split_k < 0 ||
+      cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0)
+    return fail(TONE_EINVAL, "tuning field out of range (lanes 0..4, persist_mode 0..3, split_k 0..%d)", (int)MAX_SPLITS);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(TONE_EINVAL, "device %d of %d", cfg->device, ndev);
@@ -307,19 +340,42 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10)
     return fail(TONE_ECUDA, "this library is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
-
   tone_engine* e = new tone_engine();
+  const int rc = create_impl(e, cfg, prop);
+  if (rc) {           // every failure path releases what was allocated so far (g_err keeps the reason)
+    tone_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return TONE_OK;
+}
+
+template <typename Tp>
+static int pinned_alloc(Tp** p, size_t n) {
+  CK(cudaMallocHost((void**)p, std::max<size_t>(n * sizeof(Tp), 64)));
+  memset(*p, 0, std::max<size_t>(n * sizeof(Tp), 64));
+  return 0;
+}
+
+static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceProp& prop) {
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("TONE_PDL")) e->pdl = atoi(v) != 0;
-  if (const char* v = getenv("TONE_FUSE_DW")) e->fuse_dw = atoi(v) != 0;
-  if (const char* v = getenv("TONE_FUSE_VATT")) e->fuse_vatt = atoi(v) != 0;
-  if (const char* v = getenv("TONE_PERSIST_MODE")) e->persist_mode = atoi(v);
+  e->pdl = !(cfg->flags & TONE_FLAG_NO_PDL);
+  e->fuse_vatt = !(cfg->flags & TONE_FLAG_NO_FUSED_VATT);
+  e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
+  e->split_k = cfg->split_k;
+  if (cfg->lanes) e->n_lanes = cfg->lanes;
+  if (cfg->lane_min_batch) e->lane_min_batch = cfg->lane_min_batch;
   e->C = cfg->chunk_samples;
   e->F = e->C / HOP;
   e->T = (e->F + SUB2_ROWS - 11) / 3 + 1;
   e->T2 = (e->T + 1 - 3) / 2 + 1;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_cap, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qr;
@@ -342,22 +398,49 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   rc |= dev_alloc(e, &e->st_conv, S * N_LAYERS * CONV_S * D_MODEL);
   rc |= dev_alloc(e, &e->st_red, S * D_MODEL);
   rc |= dev_alloc(e, &e->st_len, S);
+  rc |= dev_alloc(e, &e->st_ph, S);
+  rc |= dev_alloc(e, &e->st_ring, S * PH_CAP);
   if (rc) return rc;
   e->slot_used.assign(S, 0);
+  e->slot_stamp.assign(S, 0);
   for (int i = (int)S - 1; i >= 0; --i) e->free_slots.push_back(i);
 
   const size_t Bm = cfg->max_batch;
   e->rows_alloc = (int)(((Bm * MAX_T + 127) / 128) * 128);
   const size_t R = e->rows_alloc;
-  rc |= dev_alloc(e, &e->d_slots, Bm);
-  rc |= dev_alloc(e, &e->d_pcm, Bm * e->C);
-  rc |= dev_alloc(e, &e->d_len_in, Bm);
+  // phrase area of one set: header | PH_PER_STREAM records per stream | text pool (a stream's buffer never exceeds
+  // ~2050 frames, plus 6 frames of overlap per phrase)
+  e->ph_bytes = sizeof(PhHeader) + Bm * PH_PER_STREAM * sizeof(PhRecord) + Bm * 2304;
+  for (int k = 0; k <= tone_engine::PIPE; ++k) {
+    tone_engine::IoSet& io = e->io[k];
+    const size_t pcm_bytes = Bm * e->C * (k == tone_engine::PIPE ? 4 : 2);
+    rc |= dev_alloc(e, &io.d_slots, Bm);
+    rc |= dev_alloc(e, (char**)&io.d_pcm, pcm_bytes);
+    rc |= dev_alloc(e, &io.d_last, Bm);
+    rc |= dev_alloc(e, &io.d_len_in, Bm);
+    rc |= dev_alloc(e, &io.d_tokens, R);
+    rc |= dev_alloc(e, &io.d_aux, R * 2);
+    rc |= dev_alloc(e, &io.d_logprobs, R * N_CLASSES);
+    rc |= dev_alloc(e, &io.d_ph, e->ph_bytes);
+    if (rc) return rc;
+    RC(pinned_alloc(&io.p_slots, Bm));
+    RC(pinned_alloc(&io.p_pcm, Bm * e->C));
+    RC(pinned_alloc(&io.p_last, Bm));
+    RC(pinned_alloc(&io.p_tokens, Bm * MAX_T));
+    RC(pinned_alloc(&io.p_logprobs, Bm * MAX_T * N_CLASSES));
+    RC(pinned_alloc(&io.p_aux, Bm * MAX_T * 2));
+    RC(pinned_alloc(&io.p_ph, e->ph_bytes));
+    CK(cudaEventCreateWithFlags(&io.ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io.ev_step, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io.ev_out, cudaEventDisableTiming));
+  }
   rc |= dev_alloc(e, &e->d_feats, Bm * N_MELS * MAX_FRAMES);
-  rc |= dev_alloc(e, &e->d_tokens, R);
-  rc |= dev_alloc(e, &e->d_aux, R * 2);
-  rc |= dev_alloc(e, &e->logprobs, R * N_CLASSES);
-  if (const char* v = getenv("TONE_LANES")) e->n_lanes = std::max(1, std::min(8, atoi(v)));
-  if (const char* v = getenv("TONE_LANE_MIN_BATCH")) e->lane_min_batch = std::max(1, atoi(v));
+  RC(pinned_alloc(&e->p_feats, Bm * N_MELS * MAX_FRAMES));
+  rc |= dev_alloc(e, &e->d_ring, (size_t)tone_engine::RING * std::max<size_t>(Bm, STATE_IO_CHUNK));
+  RC(pinned_alloc(&e->p_ring, (size_t)tone_engine::RING * std::max<size_t>(Bm, STATE_IO_CHUNK)));
+  for (int i = 0; i < tone_engine::RING; ++i) CK(cudaEventCreateWithFlags(&e->ev_ring[i], cudaEventDisableTiming));
+  rc |= dev_alloc(e, &e->d_state_io, (size_t)STATE_IO_CHUNK * TONE_STATE_SIZE);
+  RC(pinned_alloc(&e->p_state_io, (size_t)STATE_IO_CHUNK * TONE_STATE_SIZE));
   e->lanes.resize(e->n_lanes);
   for (int li = 0; li < e->n_lanes; ++li) {
     tone_engine::Lane& ln = e->lanes[li];
@@ -383,12 +466,6 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   }
   CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
   if (rc) return rc;
-  CK(cudaMallocHost((void**)&e->p_slots, Bm * 4));
-  CK(cudaMallocHost((void**)&e->p_pcm, Bm * e->C * 4));
-  CK(cudaMallocHost((void**)&e->p_tokens, Bm * MAX_T * 4));
-  CK(cudaMallocHost((void**)&e->p_logprobs, Bm * MAX_T * N_CLASSES * 4));
-  CK(cudaMallocHost((void**)&e->p_aux, Bm * MAX_T * 2 * 4));
-  CK(cudaMallocHost((void**)&e->p_feats, Bm * N_MELS * MAX_FRAMES * 2));
 
   // activation-side tensor maps
   {
@@ -434,7 +511,6 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc<G_KV, BN_KV>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
-  CK((configure_gemm_tc<G_GLU_DW, BN_GLU>()));
   CK((configure_gemm_tc<G_VATT, D_HEAD>()));
   CK((configure_gemm_tc<G_RESID, 128>()));
   CK((configure_gemm_tc<G_GLU, 128>()));
@@ -448,34 +524,47 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   CK((configure_gemm_tc_persist<G_STORE_F32, 1, false>()));
   CK((configure_gemm_tc_persist<G_PARTIAL, 1, false>()));
   e->persist_ctas = e->num_sms;
-  e->persist_min_tiles = e->num_sms + 1;
-  if (const char* v = getenv("TONE_PERSIST_CTAS")) e->persist_ctas = std::max(2, atoi(v));
-  if (const char* v = getenv("TONE_PERSIST_MIN_TILES")) e->persist_min_tiles = atoi(v);
+  e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-  CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine stream is non-blocking
-  *out = e;
+  CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine streams are non-blocking
   return TONE_OK;
 }
 
 extern "C" void tone_destroy(tone_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (auto& ln : e->lanes) {
     if (ln.stream) cudaStreamDestroy(ln.stream);
     if (ln.done) cudaEventDestroy(ln.done);
   }
   if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+  if (e->ev_sync) cudaEventDestroy(e->ev_sync);
+  if (e->ev_last) cudaEventDestroy(e->ev_last);
+  for (int i = 0; i < tone_engine::RING; ++i)
+    if (e->ev_ring[i]) cudaEventDestroy(e->ev_ring[i]);
   for (void* p : e->allocs) cudaFree(p);
-  cudaFree(e->w_arena);
-  cudaFreeHost(e->p_slots);
-  cudaFreeHost(e->p_pcm);
-  cudaFreeHost(e->p_tokens);
-  cudaFreeHost(e->p_logprobs);
-  cudaFreeHost(e->p_aux);
-  cudaFreeHost(e->p_feats);
-  cudaStreamDestroy(e->stream);
+  if (e->w_arena) cudaFree(e->w_arena);
+  for (auto& io : e->io) {
+    if (io.p_slots) cudaFreeHost(io.p_slots);
+    if (io.p_pcm) cudaFreeHost(io.p_pcm);
+    if (io.p_last) cudaFreeHost(io.p_last);
+    if (io.p_tokens) cudaFreeHost(io.p_tokens);
+    if (io.p_logprobs) cudaFreeHost(io.p_logprobs);
+    if (io.p_aux) cudaFreeHost(io.p_aux);
+    if (io.p_ph) cudaFreeHost(io.p_ph);
+    if (io.ev_in) cudaEventDestroy(io.ev_in);
+    if (io.ev_step) cudaEventDestroy(io.ev_step);
+    if (io.ev_out) cudaEventDestroy(io.ev_out);
+  }
+  if (e->p_feats) cudaFreeHost(e->p_feats);
+  if (e->p_ring) cudaFreeHost(e->p_ring);
+  if (e->p_state_io) cudaFreeHost(e->p_state_io);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
+  if (e->s_cap) cudaStreamDestroy(e->s_cap);
   delete e;
 }
 
@@ -492,6 +581,8 @@ extern "C" int tone_get_info(const tone_engine* e, tone_info* o) {
   o->state_bytes_per_slot = (int64_t)HOP * 2 + FEAT_ROWS_MAX * N_MELS * 2 + (int64_t)X1_ROWS_MAX * X1_ROW * 2 +
                             2LL * KV_ROWS_MAX * D_MODEL * 2 + (int64_t)N_LAYERS * CONV_S * D_MODEL * 2 + D_MODEL * 4 + 4;
   o->weight_bytes = (int64_t)e->w_used;
+  o->pipeline_depth = tone_engine::PIPE;
+  o->max_phrases_per_step = PH_PER_STREAM * e->cfg.max_batch;
   return TONE_OK;
 }
 
@@ -773,8 +864,6 @@ static int finalize_layer(tone_engine* e, int l) {
     if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, BN_GLU / 2), &L.pw1_b))) return rc;
     if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, 64), 2 * D_MODEL, D_MODEL, 128, &L.pw1w))) return rc;
     if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, 64), &L.pw1w_b))) return rc;
-    if ((rc = upload_mat(e, interleave_rows(a, b, D_MODEL, D_MODEL, 48), 2 * D_MODEL, D_MODEL, 96, &L.pw1c))) return rc;
-    if ((rc = upload_f32(e, interleave_rows(ab, bb, D_MODEL, 1, 48), &L.pw1c_b))) return rc;
   }
   NEEDW(dw, Cp + "depthwise_conv.conv.weight");
   NEEDW(dwb, Cp + "depthwise_conv.conv.bias");
@@ -791,178 +880,6 @@ static int finalize_layer(tone_engine* e, int l) {
   NEEDW(p2b, Cp + "pointwise_conv2.bias");
   if ((rc = upload_mat(e, p2->data, D_MODEL, D_MODEL, BN_RESID, &L.pw2))) return rc;
   if ((rc = upload_f32(e, p2b->data, &L.pw2_b))) return rc;
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ cluster (latency) path
-template <int T_, int G_>
-static cudaError_t launch_cluster_t(cudaStream_t st, int n_clusters, const ClParams* dp, const ClStep& step) {
-  using Cfg = ClCfg<T_, G_>;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(n_clusters * CL_CTAS);
-  cfg.blockDim = dim3(CL_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL_CTAS;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, encoder_cluster_kernel<T_, G_>, dp, step);
-}
-
-template <int T_, int G_>
-static int configure_cluster_t(tone_engine* e, int which) {
-  using Cfg = ClCfg<T_, G_>;
-  CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(encoder_cluster_kernel<T_, G_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(CL_CTAS * 64);
-  cfg.blockDim = dim3(CL_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL_CTAS;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  int nc = 0;
-  CK(cudaOccupancyMaxActiveClusters(&nc, encoder_cluster_kernel<T_, G_>, &cfg));
-  e->cluster_max_active[which] = nc;
-  e->cluster_Gs[which] = G_;
-  return 0;
-}
-
-static int finalize_cluster(tone_engine* e) {
-  e->cluster_max_batch = e->cfg.cluster_max_batch;
-  if (const char* v = getenv("TONE_CLUSTER_MAX_B")) e->cluster_max_batch = atoi(v);
-  if (e->cfg.gemm_impl != 0) e->cluster_max_batch = 0;
-  int rc;
-  std::vector<CUtensorMap> maps(CG_TOTAL);
-  auto wm = [&](int idx, const WeightMat& w, int box_rows) -> int {
-    return make_map_2d(e, &maps[idx], w.ptr, w.N, w.K, box_rows, true);
-  };
-  for (int l = 0; l < N_LAYERS; ++l) {
-    LayerW& L = e->L[l];
-    const int b = l * CM_PER_LAYER;
-    if ((rc = wm(b + CM_FF1_UP, L.ff1_up, 64))) return rc;
-    if ((rc = wm(b + CM_FF1_DOWN, L.ff1_down, 128))) return rc;
-    if ((rc = wm(b + CM_QKV, l < 14 ? L.qkv : L.q, 48))) return rc;
-    if ((rc = wm(b + CM_KV, l < 14 ? L.qkv : L.kv, 48))) return rc;
-    if ((rc = wm(b + CM_WO, L.wo, 128))) return rc;
-    if ((rc = wm(b + CM_PW1, L.pw1c, 96))) return rc;
-    if ((rc = wm(b + CM_PW2, L.pw2, 128))) return rc;
-    if ((rc = wm(b + CM_FF2_UP, L.ff2_up, 64))) return rc;
-    if ((rc = wm(b + CM_FF2_DOWN, L.ff2_down, 128))) return rc;
-  }
-  if ((rc = wm(CG_RED_PW, e->red_pw, 128))) return rc;
-  if ((rc = wm(CG_DEC, e->dec_w, 48))) return rc;
-  {
-    const uint64_t S = e->cfg.max_slots;
-    uint64_t d[3] = {D_MODEL, KV_ROWS_MAX, S}, s[2] = {D_MODEL * 2, (uint64_t)KV_ROWS_MAX * D_MODEL * 2};
-    uint32_t b14[3] = {64, MHSA_S / 2, 1}, b15[3] = {64, MHSA_S, 1};
-    if ((rc = make_map(e, &maps[CG_KVC14], e->st_kv14, 3, d, s, b14, false))) return rc;
-    if ((rc = make_map(e, &maps[CG_KVC15], e->st_kv15, 3, d, s, b15, false))) return rc;
-  }
-  rc = dev_alloc(e, &e->d_cl_maps, (size_t)CG_TOTAL);
-  if (rc) return rc;
-  CK(cudaMemcpy(e->d_cl_maps, maps.data(), sizeof(CUtensorMap) * CG_TOTAL, cudaMemcpyHostToDevice));
-  ClParams p;
-  memset(&p, 0, sizeof(p));
-  p.maps = e->d_cl_maps;
-  for (int l = 0; l < N_LAYERS; ++l) {
-    LayerW& L = e->L[l];
-    ClLayer& c = p.L[l];
-    c.ff1_up_b = L.ff1_up_b;
-    c.ff1_down_b = L.ff1_down_b;
-    c.ff2_up_b = L.ff2_up_b;
-    c.ff2_down_b = L.ff2_down_b;
-    c.qkv_b = L.qkv_b;
-    c.q_b = L.q_b;
-    c.kv_b = L.kv_b;
-    c.wo_b = L.wo_b;
-    c.pw1_b = L.pw1c_b;
-    c.pw2_b = L.pw2_b;
-    c.g_ff1 = L.n_ff1;
-    c.g_att = L.n_att;
-    c.g_out = L.n_out;
-    c.qln_w = L.qln_w;
-    c.qln_b = L.qln_b;
-    c.kln_w = L.kln_w;
-    c.kln_b = L.kln_b;
-    c.dw_w = L.dw_w;
-    c.dw_b = L.dw_b;
-  }
-  p.red_dw_w = e->red_dw_w;
-  p.red_dw_b = e->red_dw_b;
-  p.red_pw_b = e->red_pw_b;
-  p.dec_b = e->dec_b;
-  p.rope_cos = e->rope_cos;
-  p.rope_sin = e->rope_sin;
-  p.kv14 = e->st_kv14;
-  p.kv15 = e->st_kv15;
-  p.conv = e->st_conv;
-  p.red = e->st_red;
-  rc = dev_alloc(e, (char**)&e->d_clp, sizeof(ClParams));
-  if (rc) return rc;
-  CK(cudaMemcpy(e->d_clp, &p, sizeof(p), cudaMemcpyHostToDevice));
-  if (e->T == 10) {
-    if ((rc = configure_cluster_t<10, 4>(e, 0))) return rc;
-    rc = configure_cluster_t<10, 5>(e, 1);
-  } else {
-    if ((rc = configure_cluster_t<13, 3>(e, 0))) return rc;
-    rc = configure_cluster_t<13, 4>(e, 1);
-  }
-  if (rc) return rc;
-  e->cluster_ok = e->cluster_max_active[0] > 0 && e->cluster_max_active[1] > 0;
-  if (getenv("TONE_CL_PROF") && atoi(getenv("TONE_CL_PROF"))) {
-    if ((rc = dev_alloc(e, &e->d_cl_prof, (size_t)6144))) return rc;
-  }
-  return 0;
-}
-
-// Diagnostics: timeline of the last cluster-kernel launch (TONE_CL_PROF=1) and the occupancy the driver reported.
-extern "C" int tone_cluster_prof_read(tone_engine* e, unsigned long long* out /* [6144] */, int32_t* max_active) {
-  if (!e) return fail(TONE_EINVAL, "null engine");
-  if (max_active) *max_active = e->cluster_max_active[0] * 1000 + e->cluster_max_active[1];
-  if (out) {
-    if (!e->d_cl_prof) return fail(TONE_ESTATE, "TONE_CL_PROF was not set when the engine was created");
-    CK(cudaSetDevice(e->cfg.device));
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, e->d_cl_prof, 6144 * 8, cudaMemcpyDeviceToHost));
-  }
-  return TONE_OK;
-}
-
-static int run_cluster(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t st, float* d_taps) {
-  ClStep s;
-  memset(&s, 0, sizeof(s));
-  s.slots = ln.slots;
-  s.len_in = ln.len_in;
-  s.r_in = ln.r_full;
-  s.res = ln.r_red;
-  s.logprobs = ln.lp_out;
-  s.tokens = ln.tok_out;
-  s.aux = ln.aux_out;
-  s.taps = d_taps;
-  s.tap_stride = (long long)e->rows_alloc * D_MODEL;
-  s.B = B;
-  s.prof = e->d_cl_prof;
-  // the smaller group size if all groups are co-resident (one wave), else the larger one
-  int which = ((B + e->cluster_Gs[0] - 1) / e->cluster_Gs[0] <= e->cluster_max_active[0]) ? 0 : 1;
-  if (const char* v = getenv("TONE_CLUSTER_G")) which = atoi(v) == e->cluster_Gs[1] ? 1 : 0;
-  const int G = e->cluster_Gs[which];
-  const int nc = std::min((B + G - 1) / G, e->cluster_max_active[which]);
-  cudaError_t err;
-  if (e->T == 10) err = which ? launch_cluster_t<10, 5>(st, nc, e->d_clp, s) : launch_cluster_t<10, 4>(st, nc, e->d_clp, s);
-  else err = which ? launch_cluster_t<13, 4>(st, nc, e->d_clp, s) : launch_cluster_t<13, 3>(st, nc, e->d_clp, s);
-  e->launches++;
-  if (err != cudaSuccess) return fail(TONE_ECUDA, "cluster kernel launch: %s", cudaGetErrorString(err));
   return 0;
 }
 
@@ -995,31 +912,73 @@ extern "C" int tone_finalize_weights(tone_engine* e) {
     if ((rc = upload_f32(e, db->data, &e->dec_b))) return rc;
   }
   e->host_w.clear();
-  if ((rc = finalize_cluster(e))) return rc;
   CK(cudaDeviceSynchronize());   // pageable H2D copies may still be in flight when cudaMemcpy returns
   e->finalized = true;
   return TONE_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ slots
+static StatePool state_pool(tone_engine* e) {
+  StatePool p;
+  p.pre = e->st_pre;
+  p.feat = e->st_feat;
+  p.x1 = e->st_x1;
+  p.kv14 = e->st_kv14;
+  p.kv15 = e->st_kv15;
+  p.conv = e->st_conv;
+  p.red = e->st_red;
+  p.len = e->st_len;
+  p.ph = e->st_ph;
+  p.F = e->F;
+  p.T = e->T;
+  p.T2 = e->T2;
+  return p;
+}
+
+// Range / allocation / uniqueness of the slot ids of one batch (O(B): a per-engine stamp array).
+static int validate_slots(tone_engine* e, int n, const int32_t* slots, bool need_alloc = true) {
+  if (++e->stamp_gen == 0) {                       // wrapped: restart the stamps
+    std::fill(e->slot_stamp.begin(), e->slot_stamp.end(), 0u);
+    e->stamp_gen = 1;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int sl = slots[i];
+    if (sl < 0 || sl >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range [0, %d)", sl, e->cfg.max_slots);
+    if (need_alloc && !e->slot_used[sl]) return fail(TONE_ESTATE, "slot %d is not allocated", sl);
+    if (e->slot_stamp[sl] == e->stamp_gen) return fail(TONE_EINVAL, "slot %d appears twice in one batch", sl);
+    e->slot_stamp[sl] = e->stamp_gen;
+  }
+  return 0;
+}
+
+// Slot ids for an asynchronous kernel: through a small pinned ring (an entry is reused only after the copy that read
+// it has completed), H2D on `st`.  Returns the device pointer through *d.
+static int ring_slots(tone_engine* e, int n, const int32_t* slots, cudaStream_t st, int** d) {
+  const size_t cap = std::max<size_t>(e->cfg.max_batch, STATE_IO_CHUNK);
+  if ((size_t)n > cap) return fail(TONE_EINVAL, "%d slots exceed the staging capacity %zu", n, cap);
+  const int k = e->ring_pos;
+  e->ring_pos = (k + 1) % tone_engine::RING;
+  CK(cudaEventSynchronize(e->ev_ring[k]));
+  memcpy(e->p_ring + k * cap, slots, (size_t)n * 4);
+  CK(cudaMemcpyAsync(e->d_ring + k * cap, e->p_ring + k * cap, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e->ev_ring[k], st));
+  *d = e->d_ring + k * cap;
+  return 0;
+}
+
 extern "C" int tone_reset_slots(tone_engine* e, int32_t n, const int32_t* slots) {
   if (!e || !slots || n < 0) return fail(TONE_EINVAL, "bad argument");
   CK(cudaSetDevice(e->cfg.device));
-  for (int i = 0; i < n; ++i) {
-    const size_t s = slots[i];
-    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slots[i]);
-    CK(cudaMemsetAsync(e->st_pre + s * HOP, 0, HOP * 2, e->stream));
-    CK(cudaMemsetAsync(e->st_feat + s * FEAT_ROWS_MAX * N_MELS, 0, FEAT_ROWS_MAX * N_MELS * 2, e->stream));
-    CK(cudaMemsetAsync(e->st_x1 + s * X1_ROWS_MAX * X1_ROW, 0, (size_t)X1_ROWS_MAX * X1_ROW * 2, e->stream));
-    CK(cudaMemsetAsync(e->st_kv14 + s * KV_ROWS_MAX * D_MODEL, 0, KV_ROWS_MAX * D_MODEL * 2, e->stream));
-    CK(cudaMemsetAsync(e->st_kv15 + s * KV_ROWS_MAX * D_MODEL, 0, KV_ROWS_MAX * D_MODEL * 2, e->stream));
-    CK(cudaMemsetAsync(e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, 0, (size_t)N_LAYERS * CONV_S * D_MODEL * 2,
-                       e->stream));
-    CK(cudaMemsetAsync(e->st_red + s * D_MODEL, 0, D_MODEL * 4, e->stream));
-    CK(cudaMemsetAsync(e->st_len + s, 0, 4, e->stream));
+  RC(validate_slots(e, n, slots, false));
+  const int cap = (int)std::max<size_t>(e->cfg.max_batch, STATE_IO_CHUNK);
+  for (int i0 = 0; i0 < n; i0 += cap) {
+    const int m = std::min(cap, n - i0);
+    int* d = nullptr;
+    RC(ring_slots(e, m, slots + i0, e->stream, &d));
+    reset_slots_kernel<<<m, STATE_IO_THREADS, 0, e->stream>>>(state_pool(e), d);
+    CK(cudaGetLastError());
   }
-  CK(cudaStreamSynchronize(e->stream));
-  return TONE_OK;
+  return TONE_OK;   // stream-ordered before any later step of this engine
 }
 
 extern "C" int tone_alloc_slots(tone_engine* e, int32_t n, int32_t* out) {
@@ -1036,9 +995,8 @@ extern "C" int tone_alloc_slots(tone_engine* e, int32_t n, int32_t* out) {
 
 extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slots) {
   if (!e || !slots || n < 0) return fail(TONE_EINVAL, "bad argument");
+  RC(validate_slots(e, n, slots));
   for (int i = 0; i < n; ++i) {
-    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
-      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
     e->slot_used[slots[i]] = 0;
     e->free_slots.push_back(slots[i]);
   }
@@ -1093,11 +1051,6 @@ static GemmArgs dense_args(int M, int K, const bf16* A, void* out, int ldo, cons
   return a;
 }
 
-#define RC(x)              \
-  do {                     \
-    int _rc = (x);         \
-    if (_rc) return _rc;   \
-  } while (0)
 #define KLAUNCH(call)                                                                                   \
   do {                                                                                                  \
     e->launches++;                                                                                      \
@@ -1136,7 +1089,7 @@ static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M,
   RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ss_tiles ? ln.m_rb : ln.m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
   int splits = 1;
   while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
-  if (const char* v = getenv("TONE_SPLITK")) splits = atoi(v);
+  if (e->split_k) splits = e->split_k;
   splits = std::max(1, std::min(splits, std::min(e->max_splits, (int)MAX_SPLITS)));
   GemmArgs b = dense_args(M, D_FF / splits, ln.h, ln.part, D_MODEL, nullptr, 1.f);
   b.lda = D_FF;
@@ -1190,6 +1143,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     memset(&a, 0, sizeof(a));
     a.slots = ln.slots;
     a.pcm = ln.pcm;
+    a.pcm_fmt = ln.pcm_fmt;
     a.feats_in = ln.feats;
     a.pre = e->st_pre;
     a.feat = e->st_feat;
@@ -1255,19 +1209,6 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
   }
   RC(run_norm(e, ln, st, ln.r_full, e->out_norm_g, e->L[0].n_ff1, ln.n, M));
   RC(tap(0, ln.r_full, M));
-
-  if (e->cluster_ok && B <= e->cluster_max_batch) {
-    // latency path: layers 0..15 and the decoder in one cluster kernel
-    if (taps && !e->d_taps) RC(dev_alloc(e, &e->d_taps, (size_t)17 * e->rows_alloc * D_MODEL));
-    RC(run_cluster(e, ln, B, st, taps ? e->d_taps : nullptr));
-    if (taps) {
-      CK(cudaStreamSynchronize(st));
-      for (int l = 0; l < N_LAYERS; ++l)
-        CK(cudaMemcpy(taps + (size_t)(1 + l) * B * T * D_MODEL, e->d_taps + (size_t)(1 + l) * e->rows_alloc * D_MODEL,
-                      (size_t)B * T * D_MODEL * 4, cudaMemcpyDeviceToHost));
-    }
-    return 0;
-  }
 
   for (int l = 0; l < N_LAYERS; ++l) {
     LayerW& L = e->L[l];
@@ -1374,21 +1315,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     int ss_tiles = 0;
     RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));
     // ---- convolution module: norm_conv is applied as a row scale inside the pointwise-conv GEMM (A = bf16(r))
-    if (e->cfg.gemm_impl == 0 && e->fuse_dw) {
-      // pointwise conv 1 + GLU + causal depthwise conv + BN + SiLU + cache roll in ONE kernel: tiles hold whole streams
-      GemmArgs a = dense_args(B, D_MODEL, ln.rb, ln.ebuf, D_MODEL, L.pw1_b, 1.f);
-      a.ss = ln.ss;
-      a.ss_ld = 12;
-      a.ss_tiles = ss_tiles;
-      a.R = Tl;
-      a.G = std::min(128 / Tl, 12);      // whole streams per tile; each epilogue warp keeps 3 cache columns in registers
-      a.slots = ln.slots;
-      a.dw_cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;
-      a.dw_cache_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
-      a.dw_w = L.dw_w;
-      a.dw_b = L.dw_b;
-      RC((gemm<G_GLU_DW, BN_GLU>(e, st, ln.m_rb, L.pw1, a, (B + a.G - 1) / a.G, 2 * D_MODEL / BN_GLU, M, D_MODEL)));
-    } else {
+    {
       {
         GemmArgs a = dense_args(M, D_MODEL, ln.rb, ln.g, D_MODEL, M >= BIG_M ? L.pw1w_b : L.pw1_b, 1.f);
         a.ss = ln.ss;
@@ -1455,26 +1382,30 @@ static int check_step_args(tone_engine* e, int B) {
   return 0;
 }
 
+enum StepMode : int { SM_FEATURES = 1, SM_PHRASES = 2, SM_PCM16 = 4 };
+
 // Cut the batch into lanes and enqueue their kernel chains: lane 0 on `st`, the others on their own streams between
-// a fork event and per-lane join events (works both eagerly and under stream capture).
-static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps, bool features = false) {
+// a fork event and per-lane join events (works both eagerly and under stream capture).  Inputs / outputs are those of
+// staging set `io`.
+static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStream_t st, float* taps, int mode) {
   int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
-  if (const char* v = getenv("TONE_FORCE_LANES")) nl = std::max(1, std::min(e->n_lanes, atoi(v)));
   nl = std::min(nl, B);
   e->launches = 0;
   const int per = (B + nl - 1) / nl;
+  const int pcm_fmt = (mode & SM_PCM16) ? 1 : 0;
   if (nl > 1) CK(cudaEventRecord(e->fork_ev, st));
   for (int li = 0; li < nl; ++li) {
     tone_engine::Lane& ln = e->lanes[li];
     const int b0 = li * per, nb = std::min(per, B - b0);
     if (nb <= 0) continue;
-    ln.slots = e->d_slots + b0;
-    ln.pcm = e->d_pcm + (size_t)b0 * e->C;
-    ln.feats = features ? e->d_feats + (size_t)b0 * N_MELS * e->F : nullptr;
-    ln.len_in = e->d_len_in + b0;
-    ln.lp_out = e->logprobs + (size_t)b0 * e->T * N_CLASSES;
-    ln.tok_out = e->d_tokens + (size_t)b0 * e->T;
-    ln.aux_out = e->d_aux + (size_t)b0 * e->T * 2;
+    ln.slots = io.d_slots + b0;
+    ln.pcm = (const char*)io.d_pcm + (size_t)b0 * e->C * (pcm_fmt ? 2 : 4);
+    ln.pcm_fmt = pcm_fmt;
+    ln.feats = (mode & SM_FEATURES) ? e->d_feats + (size_t)b0 * N_MELS * e->F : nullptr;
+    ln.len_in = io.d_len_in + b0;
+    ln.lp_out = io.d_logprobs + (size_t)b0 * e->T * N_CLASSES;
+    ln.tok_out = io.d_tokens + (size_t)b0 * e->T;
+    ln.aux_out = io.d_aux + (size_t)b0 * e->T * 2;
     cudaStream_t ls = li == 0 ? st : ln.stream;
     if (li > 0) CK(cudaStreamWaitEvent(ls, e->fork_ev, 0));
     RC(run_step(e, ln, nb, ls, taps));
@@ -1483,75 +1414,277 @@ static int enqueue_step(tone_engine* e, int B, cudaStream_t st, float* taps, boo
       CK(cudaStreamWaitEvent(st, ln.done, 0));
     }
   }
+  if (mode & SM_PHRASES) {   // device-side phrase splitter + greedy decode over the whole batch (after the lanes joined)
+    PhraseArgs pa;
+    pa.slots = io.d_slots;
+    pa.tokens = io.d_tokens;
+    pa.sil = io.d_aux;
+    pa.is_last = io.d_last;
+    pa.st = e->st_ph;
+    pa.ring = e->st_ring;
+    pa.hdr = reinterpret_cast<PhHeader*>(io.d_ph);
+    pa.rec = reinterpret_cast<PhRecord*>(io.d_ph + sizeof(PhHeader));
+    pa.pool = reinterpret_cast<unsigned char*>(io.d_ph + sizeof(PhHeader) + (size_t)B * PH_PER_STREAM * sizeof(PhRecord));
+    pa.B = B;
+    pa.T = e->T;
+    pa.max_rec = B * PH_PER_STREAM;
+    pa.pool_cap = B * 2304;
+    KLAUNCH(launch_kernel(ctc_phrase_kernel, dim3(1), dim3(PH_THREADS), 0, st, e->pdl, pa));
+  }
   e->launches_per_step = e->launches;
   return 0;
 }
 
-static int launch_step(tone_engine* e, int B, cudaStream_t st, bool features = false) {
-  if (!e->cfg.use_graph) return enqueue_step(e, B, st, nullptr, features);
-  const int key = B + (features ? (1 << 24) : 0);
+// Replay (or capture on first use) the step graph of (batch size, staging set, mode) on `st`.
+static int launch_step(tone_engine* e, int set, int B, cudaStream_t st, int mode) {
+  tone_engine::IoSet& io = e->io[set];
+  if (!e->cfg.use_graph) return enqueue_step(e, io, B, st, nullptr, mode);
+  const uint64_t key = (uint64_t)B | ((uint64_t)set << 24) | ((uint64_t)mode << 28);
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
-    cudaGraph_t graph;
-    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(e, B, e->stream, nullptr, features);
-    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
-    if (rc) return rc;
-    if (ce != cudaSuccess) return fail(TONE_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
-    cudaGraphExec_t exec;
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    CK(cudaGraphDestroy(graph));
+    // Capture on a side stream that has nothing in flight, so the capture neither depends on nor disturbs `st`.
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cs = e->s_cap;
+    CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(e, io, B, cs, nullptr, mode);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc ? rc : fail(TONE_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+    }
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(TONE_ECUDA, "graph instantiate: %s", cudaGetErrorString(ie));
+    if (e->graphs.size() >= 64) {   // bound the cache: a dynamic batcher can name many batch sizes
+      CK(cudaStreamSynchronize(e->stream));
+      for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+      e->graphs.clear();
+    }
     it = e->graphs.emplace(key, exec).first;
   }
   CK(cudaGraphLaunch(it->second, st));
   return 0;
 }
 
+// A launch on a caller's stream is spliced into the engine's timeline: the caller's stream first waits for everything
+// the engine has enqueued so far (staging copies, the previous step), and the engine's stream then waits for the launch.
+static int splice_begin(tone_engine* e, cudaStream_t st) {
+  if (st == e->stream) return 0;
+  CK(cudaEventRecord(e->ev_sync, e->stream));
+  CK(cudaStreamWaitEvent(st, e->ev_sync, 0));
+  return 0;
+}
+static int splice_end(tone_engine* e, cudaStream_t st) {
+  if (st == e->stream) return 0;
+  CK(cudaEventRecord(e->ev_last, st));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_last, 0));
+  return 0;
+}
+
+// int32 samples -> the int16 wire format, range-checked (tone/onnx_wrapper.py:108-113)
+static int narrow_pcm(const int32_t* src, int16_t* dst, size_t n) {
+  int32_t lo = n ? src[0] : 0, hi = lo;
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t v = src[i];
+    lo = v < lo ? v : lo;
+    hi = v > hi ? v : hi;
+    dst[i] = (int16_t)v;
+  }
+  if (lo < -32768 || hi > 32767)
+    return fail(TONE_ERANGE, "Samples in 'audio_chunk' must be in range [-32768; 32767], but it is in range [%d; %d]", (int)lo, (int)hi);
+  return 0;
+}
+
+static inline tone_engine::IoSet& legacy_set(tone_engine* e) { return e->io[tone_engine::PIPE]; }
+
+// ------------------------------------------------------------------------------------------------ pipelined step
+extern "C" int tone_next_staging(tone_engine* e, int32_t** slots, int16_t** pcm16, uint8_t** is_last) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  tone_engine::IoSet& io = e->io[e->next_ticket % tone_engine::PIPE];
+  if (slots) *slots = io.p_slots;
+  if (pcm16) *pcm16 = io.p_pcm;
+  if (is_last) *is_last = io.p_last;
+  return TONE_OK;
+}
+
+extern "C" int tone_submit(tone_engine* e, int32_t B, const int32_t* slots, const void* pcm, int32_t pcm_format,
+                           const uint8_t* is_last, int32_t outputs, int32_t* ticket_out) {
+  RC(check_step_args(e, B));
+  if (!slots || !pcm || !ticket_out) return fail(TONE_EINVAL, "null argument");
+  if (pcm_format != TONE_PCM_I32 && pcm_format != TONE_PCM_I16) return fail(TONE_EINVAL, "unknown pcm_format %d", pcm_format);
+  if (outputs & ~(TONE_OUT_LOGPROBS | TONE_OUT_TOKENS | TONE_OUT_SIL | TONE_OUT_PHRASES))
+    return fail(TONE_EINVAL, "unknown output bits 0x%x", outputs);
+  CK(cudaSetDevice(e->cfg.device));
+  const int set = e->next_ticket % tone_engine::PIPE;
+  tone_engine::IoSet& io = e->io[set];
+  if (io.busy) return fail(TONE_ESTATE, "ticket %d of this staging set has not been waited for", io.ticket);
+  RC(validate_slots(e, B, slots));
+  const size_t ns = (size_t)B * e->C;
+  if (pcm_format == TONE_PCM_I32) RC(narrow_pcm((const int32_t*)pcm, io.p_pcm, ns));
+  else if (pcm != io.p_pcm) memcpy(io.p_pcm, pcm, ns * 2);
+  if (slots != io.p_slots) memcpy(io.p_slots, slots, (size_t)B * 4);
+  const bool phrases = outputs & TONE_OUT_PHRASES;
+  if (phrases) {
+    if (is_last && is_last != io.p_last) memcpy(io.p_last, is_last, B);
+    else if (!is_last) memset(io.p_last, 0, B);
+  }
+  // H2D on the input copy stream
+  CK(cudaMemcpyAsync(io.d_slots, io.p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->s_in));
+  CK(cudaMemcpyAsync(io.d_pcm, io.p_pcm, ns * 2, cudaMemcpyHostToDevice, e->s_in));
+  if (phrases) CK(cudaMemcpyAsync(io.d_last, io.p_last, B, cudaMemcpyHostToDevice, e->s_in));
+  CK(cudaEventRecord(io.ev_in, e->s_in));
+  // the step on the compute stream
+  CK(cudaStreamWaitEvent(e->stream, io.ev_in, 0));
+  RC(launch_step(e, set, B, e->stream, SM_PCM16 | (phrases ? SM_PHRASES : 0)));
+  CK(cudaEventRecord(io.ev_step, e->stream));
+  // D2H of what was asked for on the output copy stream
+  CK(cudaStreamWaitEvent(e->s_out, io.ev_step, 0));
+  const size_t rows = (size_t)B * e->T;
+  if (outputs & TONE_OUT_LOGPROBS)
+    CK(cudaMemcpyAsync(io.p_logprobs, io.d_logprobs, rows * N_CLASSES * 4, cudaMemcpyDeviceToHost, e->s_out));
+  if (outputs & TONE_OUT_TOKENS) CK(cudaMemcpyAsync(io.p_tokens, io.d_tokens, rows * 4, cudaMemcpyDeviceToHost, e->s_out));
+  if (outputs & TONE_OUT_SIL) CK(cudaMemcpyAsync(io.p_aux, io.d_aux, rows * 8, cudaMemcpyDeviceToHost, e->s_out));
+  if (phrases) {   // header + records + the first 32 KB of the text pool; the rest (rare) is fetched by tone_wait
+    const size_t fixed = sizeof(PhHeader) + (size_t)B * PH_PER_STREAM * sizeof(PhRecord);
+    const size_t n = std::min(fixed + (size_t)B * 2304, fixed + (32u << 10));
+    CK(cudaMemcpyAsync(io.p_ph, io.d_ph, n, cudaMemcpyDeviceToHost, e->s_out));
+  }
+  CK(cudaEventRecord(io.ev_out, e->s_out));
+  io.busy = true;
+  io.B = B;
+  io.outputs = outputs;
+  io.ticket = e->next_ticket++;
+  io.ph_complete = !phrases;
+  *ticket_out = io.ticket;
+  return TONE_OK;
+}
+
+extern "C" int tone_wait(tone_engine* e, int32_t ticket, float* logprobs, int32_t* tokens, float* sil) {
+  if (!e) return fail(TONE_EINVAL, "null engine");
+  tone_engine::IoSet* io = nullptr;
+  for (int k = 0; k < tone_engine::PIPE; ++k)
+    if (e->io[k].busy && e->io[k].ticket == ticket) io = &e->io[k];
+  if (!io) return fail(TONE_ESTATE, "ticket %d is not in flight", ticket);
+  if ((logprobs && !(io->outputs & TONE_OUT_LOGPROBS)) || (tokens && !(io->outputs & TONE_OUT_TOKENS)) ||
+      (sil && !(io->outputs & TONE_OUT_SIL)))
+    return fail(TONE_EINVAL, "an output was asked for that ticket %d did not request at tone_submit", ticket);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaEventSynchronize(io->ev_out));
+  io->busy = false;
+  const size_t rows = (size_t)io->B * e->T;
+  if (logprobs && logprobs != io->p_logprobs) memcpy(logprobs, io->p_logprobs, rows * N_CLASSES * 4);
+  if (tokens && tokens != io->p_tokens) memcpy(tokens, io->p_tokens, rows * 4);
+  if (sil && sil != io->p_aux) memcpy(sil, io->p_aux, rows * 8);
+  if (io->outputs & TONE_OUT_PHRASES) {
+    const PhHeader* h = reinterpret_cast<const PhHeader*>(io->p_ph);
+    if (h->overflow) return fail(TONE_ECUDA, "phrase records overflowed (%d phrases, %d text bytes)", h->n_phrases, h->pool_used);
+    const size_t fixed = sizeof(PhHeader) + (size_t)io->B * PH_PER_STREAM * sizeof(PhRecord);
+    if ((size_t)h->pool_used > (32u << 10)) {
+      CK(cudaMemcpyAsync(io->p_ph + fixed + (32u << 10), io->d_ph + fixed + (32u << 10), (size_t)h->pool_used - (32u << 10),
+                         cudaMemcpyDeviceToHost, e->s_out));
+      CK(cudaStreamSynchronize(e->s_out));
+    }
+    io->ph_complete = true;
+  }
+  return TONE_OK;
+}
+
+extern "C" int tone_ticket_phrases(tone_engine* e, int32_t ticket, const tone_phrase** phrases, int32_t* n_phrases,
+                                   const uint8_t** text_pool, int32_t* text_pool_len) {
+  if (!e || !phrases || !n_phrases || !text_pool || !text_pool_len) return fail(TONE_EINVAL, "null argument");
+  tone_engine::IoSet* io = nullptr;
+  if (ticket == -1) io = &legacy_set(e);   // tone_selftest_phrases
+  for (int k = 0; k < tone_engine::PIPE && ticket >= 0; ++k)
+    if (e->io[k].ticket == ticket) io = &e->io[k];
+  if (!io || io->busy || !io->ph_complete || !(io->outputs & TONE_OUT_PHRASES))
+    return fail(TONE_ESTATE, "ticket %d has no phrase records to read (not waited for, reused, or PHRASES not requested)", ticket);
+  static_assert(sizeof(tone_phrase) == sizeof(PhRecord), "tone_phrase layout");
+  const PhHeader* h = reinterpret_cast<const PhHeader*>(io->p_ph);
+  *phrases = reinterpret_cast<const tone_phrase*>(io->p_ph + sizeof(PhHeader));
+  *n_phrases = h->n_phrases;
+  *text_pool = reinterpret_cast<const uint8_t*>(io->p_ph + sizeof(PhHeader) + (size_t)io->B * PH_PER_STREAM * sizeof(PhRecord));
+  *text_pool_len = h->pool_used;
+  return TONE_OK;
+}
+
+// The synchronous reference-shaped call: one ticket through the same pipeline.
+extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
+                         int32_t* tokens) {
+  int ticket = -1;
+  const int outputs = (logprobs ? TONE_OUT_LOGPROBS : 0) | (tokens ? TONE_OUT_TOKENS : 0);
+  RC(tone_submit(e, B, slots, pcm, TONE_PCM_I32, nullptr, outputs, &ticket));
+  return tone_wait(e, ticket, logprobs, tokens, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ staged / device forms
 extern "C" int tone_stage(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm) {
   RC(check_step_args(e, B));
   if (!slots || !pcm) return fail(TONE_EINVAL, "null argument");
   CK(cudaSetDevice(e->cfg.device));
-  for (int i = 0; i < B; ++i)
-    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
-      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
-  if (slots != e->p_slots) memcpy(e->p_slots, slots, (size_t)B * 4);
-  if (pcm != e->p_pcm) memcpy(e->p_pcm, pcm, (size_t)B * e->C * 4);
-  CK(cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->d_pcm, e->p_pcm, (size_t)B * e->C * 4, cudaMemcpyHostToDevice, e->stream));
+  RC(validate_slots(e, B, slots));
+  tone_engine::IoSet& io = legacy_set(e);
+  CK(cudaStreamSynchronize(e->stream));     // the pinned staging of this set may still be read by an earlier copy
+  RC(narrow_pcm(pcm, io.p_pcm, (size_t)B * e->C));
+  memcpy(io.p_slots, slots, (size_t)B * 4);
+  CK(cudaMemcpyAsync(io.d_slots, io.p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(io.d_pcm, io.p_pcm, (size_t)B * e->C * 2, cudaMemcpyHostToDevice, e->stream));
+  io.B = B;
+  io.staged_mode = SM_PCM16;                // format of what is staged
   return TONE_OK;
 }
 
 extern "C" int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream) {
   RC(check_step_args(e, B));
   CK(cudaSetDevice(e->cfg.device));
-  return launch_step(e, B, cuda_stream ? (cudaStream_t)cuda_stream : e->stream);
+  tone_engine::IoSet& io = legacy_set(e);
+  if (io.B != B) return fail(TONE_ESTATE, "%d streams are staged, the step names %d", io.B, B);
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  RC(splice_begin(e, st));
+  RC(launch_step(e, tone_engine::PIPE, B, st, io.staged_mode));
+  return splice_end(e, st);
 }
 
 // Device-pointer form for GPU-resident producers/consumers: inputs are copied device-to-device into the engine's
 // staging (the captured graph reads fixed addresses), outputs are copied out the same way.  Stream-ordered, no sync.
-extern "C" int tone_step_device(tone_engine* e, int32_t B, const int32_t* d_slots, const int32_t* d_pcm,
+extern "C" int tone_step_device(tone_engine* e, int32_t B, const int32_t* slots, const void* d_pcm, int32_t pcm_format,
                                 float* d_logprobs, int32_t* d_tokens, void* cuda_stream) {
   RC(check_step_args(e, B));
+  if (!slots) return fail(TONE_EINVAL, "null argument");
+  if (pcm_format != TONE_PCM_I32 && pcm_format != TONE_PCM_I16) return fail(TONE_EINVAL, "unknown pcm_format %d", pcm_format);
   CK(cudaSetDevice(e->cfg.device));
+  RC(validate_slots(e, B, slots));
+  tone_engine::IoSet& io = legacy_set(e);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-  if (d_slots) CK(cudaMemcpyAsync(e->d_slots, d_slots, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-  if (d_pcm) CK(cudaMemcpyAsync(e->d_pcm, d_pcm, (size_t)B * e->C * 4, cudaMemcpyDeviceToDevice, st));
-  RC(launch_step(e, B, st));
+  RC(splice_begin(e, st));
+  int* ds = nullptr;
+  RC(ring_slots(e, B, slots, st, &ds));
+  CK(cudaMemcpyAsync(io.d_slots, ds, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_pcm) {
+    CK(cudaMemcpyAsync(io.d_pcm, d_pcm, (size_t)B * e->C * (pcm_format == TONE_PCM_I16 ? 2 : 4), cudaMemcpyDeviceToDevice, st));
+    io.staged_mode = pcm_format == TONE_PCM_I16 ? SM_PCM16 : 0;
+  } else if (io.B != B) {
+    return fail(TONE_ESTATE, "no PCM given and %d streams are staged, the step names %d", io.B, B);
+  }
+  io.B = B;
+  RC(launch_step(e, tone_engine::PIPE, B, st, io.staged_mode));
   if (d_logprobs)
-    CK(cudaMemcpyAsync(d_logprobs, e->logprobs, (size_t)B * e->T * N_CLASSES * 4, cudaMemcpyDeviceToDevice, st));
-  if (d_tokens) CK(cudaMemcpyAsync(d_tokens, e->d_tokens, (size_t)B * e->T * 4, cudaMemcpyDeviceToDevice, st));
-  return TONE_OK;
+    CK(cudaMemcpyAsync(d_logprobs, io.d_logprobs, (size_t)B * e->T * N_CLASSES * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_tokens) CK(cudaMemcpyAsync(d_tokens, io.d_tokens, (size_t)B * e->T * 4, cudaMemcpyDeviceToDevice, st));
+  return splice_end(e, st);
 }
 
 extern "C" int tone_fetch(tone_engine* e, int32_t B, float* logprobs, int32_t* tokens) {
   RC(check_step_args(e, B));
   CK(cudaSetDevice(e->cfg.device));
+  tone_engine::IoSet& io = legacy_set(e);
   const size_t nl = (size_t)B * e->T * N_CLASSES * 4, nt = (size_t)B * e->T * 4;
-  if (logprobs) CK(cudaMemcpyAsync(e->p_logprobs, e->logprobs, nl, cudaMemcpyDeviceToHost, e->stream));
-  if (tokens) CK(cudaMemcpyAsync(e->p_tokens, e->d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
+  // e->stream has waited for the last launch wherever it ran (splice_end), so its order covers the outputs
+  if (logprobs) CK(cudaMemcpyAsync(io.p_logprobs, io.d_logprobs, nl, cudaMemcpyDeviceToHost, e->stream));
+  if (tokens) CK(cudaMemcpyAsync(io.p_tokens, io.d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  if (logprobs && logprobs != e->p_logprobs) memcpy(logprobs, e->p_logprobs, nl);
-  if (tokens && tokens != e->p_tokens) memcpy(tokens, e->p_tokens, nt);
+  if (logprobs) memcpy(logprobs, io.p_logprobs, nl);
+  if (tokens) memcpy(tokens, io.p_tokens, nt);
   return TONE_OK;
 }
 
@@ -1561,12 +1694,13 @@ extern "C" int tone_fetch_greedy(tone_engine* e, int32_t B, int32_t* tokens, flo
   RC(check_step_args(e, B));
   if (!tokens || !sil_logprobs) return fail(TONE_EINVAL, "null argument");
   CK(cudaSetDevice(e->cfg.device));
+  tone_engine::IoSet& io = legacy_set(e);
   const size_t nt = (size_t)B * e->T * 4, na = (size_t)B * e->T * 8;
-  CK(cudaMemcpyAsync(e->p_tokens, e->d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(e->p_aux, e->d_aux, na, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(io.p_tokens, io.d_tokens, nt, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(io.p_aux, io.d_aux, na, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  memcpy(tokens, e->p_tokens, nt);
-  memcpy(sil_logprobs, e->p_aux, na);
+  memcpy(tokens, io.p_tokens, nt);
+  memcpy(sil_logprobs, io.p_aux, na);
   return TONE_OK;
 }
 
@@ -1574,56 +1708,8 @@ extern "C" int tone_sync(tone_engine* e) {
   if (!e) return fail(TONE_EINVAL, "null engine");
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_out));
   return TONE_OK;
-}
-
-// One graph for the whole host-facing call: H2D of slots + PCM from the pinned staging buffers, the step, D2H of
-// logprobs + tokens into the pinned staging buffers (one launch and one synchronise instead of six API calls).
-static int launch_step_e2e(tone_engine* e, int B) {
-  const int key = B + (2 << 24);
-  auto it = e->graphs.find(key);
-  if (it == e->graphs.end()) {
-    cudaGraph_t graph;
-    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t c1 = cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream);
-    cudaError_t c2 = cudaMemcpyAsync(e->d_pcm, e->p_pcm, (size_t)B * e->C * 4, cudaMemcpyHostToDevice, e->stream);
-    int rc = enqueue_step(e, B, e->stream, nullptr, false);
-    cudaError_t c3 = cudaMemcpyAsync(e->p_logprobs, e->logprobs, (size_t)B * e->T * N_CLASSES * 4, cudaMemcpyDeviceToHost,
-                                     e->stream);
-    cudaError_t c4 = cudaMemcpyAsync(e->p_tokens, e->d_tokens, (size_t)B * e->T * 4, cudaMemcpyDeviceToHost, e->stream);
-    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
-    if (rc) return rc;
-    if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess || ce != cudaSuccess)
-      return fail(TONE_ECUDA, "graph capture (host-facing step): %s", cudaGetErrorString(ce != cudaSuccess ? ce : c1));
-    cudaGraphExec_t exec;
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    CK(cudaGraphDestroy(graph));
-    it = e->graphs.emplace(key, exec).first;
-  }
-  CK(cudaGraphLaunch(it->second, e->stream));
-  return 0;
-}
-
-extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
-                         int32_t* tokens) {
-  if (e && e->cfg.use_graph) {
-    RC(check_step_args(e, B));
-    if (!slots || !pcm) return fail(TONE_EINVAL, "null argument");
-    CK(cudaSetDevice(e->cfg.device));
-    for (int i = 0; i < B; ++i)
-      if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
-        return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
-    if (slots != e->p_slots) memcpy(e->p_slots, slots, (size_t)B * 4);
-    if (pcm != e->p_pcm) memcpy(e->p_pcm, pcm, (size_t)B * e->C * 4);
-    RC(launch_step_e2e(e, B));
-    CK(cudaStreamSynchronize(e->stream));
-    if (logprobs && logprobs != e->p_logprobs) memcpy(logprobs, e->p_logprobs, (size_t)B * e->T * N_CLASSES * 4);
-    if (tokens && tokens != e->p_tokens) memcpy(tokens, e->p_tokens, (size_t)B * e->T * 4);
-    return TONE_OK;
-  }
-  RC(tone_stage(e, B, slots, pcm));
-  RC(launch_step(e, B, e->stream));
-  return tone_fetch(e, B, logprobs, tokens);
 }
 
 // Feature-input mode (reference skip_preprocessor=True, tone/nn/model.py:151-160; the Triton ensemble feeds DALI log-mel
@@ -1633,122 +1719,171 @@ extern "C" int tone_step_features(tone_engine* e, int32_t B, const int32_t* slot
   RC(check_step_args(e, B));
   if (!slots || !feats) return fail(TONE_EINVAL, "null argument");
   CK(cudaSetDevice(e->cfg.device));
-  for (int i = 0; i < B; ++i)
-    if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || !e->slot_used[slots[i]])
-      return fail(TONE_ESTATE, "slot %d is not allocated", slots[i]);
+  RC(validate_slots(e, B, slots));
+  tone_engine::IoSet& io = legacy_set(e);
+  CK(cudaStreamSynchronize(e->stream));
   const size_t nf = (size_t)B * N_MELS * e->F;
-  memcpy(e->p_slots, slots, (size_t)B * 4);
+  memcpy(io.p_slots, slots, (size_t)B * 4);
   memcpy(e->p_feats, feats, nf * 2);
-  CK(cudaMemcpyAsync(e->d_slots, e->p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(io.d_slots, io.p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(e->d_feats, e->p_feats, nf * 2, cudaMemcpyHostToDevice, e->stream));
-  RC(launch_step(e, B, e->stream, true));
+  io.B = 0;                                 // no PCM is staged
+  RC(launch_step(e, tone_engine::PIPE, B, e->stream, SM_FEATURES));
   return tone_fetch(e, B, logprobs, tokens);
 }
 
 extern "C" int tone_step_debug(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm, float* logprobs,
                                int32_t* tokens, float* taps) {
   RC(tone_stage(e, B, slots, pcm));
-  RC(enqueue_step(e, B, e->stream, taps));
+  RC(enqueue_step(e, legacy_set(e), B, e->stream, taps, SM_PCM16));
   return tone_fetch(e, B, logprobs, tokens);
 }
 
-// Pinned staging buffers of the engine: writing inputs / reading outputs there skips one host copy per step.
-extern "C" int tone_host_buffers(tone_engine* e, int32_t** slots, int32_t** pcm, float** logprobs, int32_t** tokens) {
-  if (!e) return fail(TONE_EINVAL, "null engine");
-  if (slots) *slots = e->p_slots;
-  if (pcm) *pcm = e->p_pcm;
-  if (logprobs) *logprobs = e->p_logprobs;
-  if (tokens) *tokens = e->p_tokens;
+// Debug: the device-side splitter alone on host-supplied per-frame inputs, `frames` frames per stream fed in pieces
+// of at most 13 (the kernel's chunk bound); is_last applies to the final piece.
+extern "C" int tone_selftest_phrases(tone_engine* e, int32_t B, const int32_t* slots, int32_t frames, const int32_t* tokens,
+                                     const float* sil, const uint8_t* is_last) {
+  RC(check_step_args(e, B));
+  if (!slots || !tokens || !sil || frames < 1 || frames > MAX_T)
+    return fail(TONE_EINVAL, "need 1 <= frames <= %d per call", (int)MAX_T);
+  CK(cudaSetDevice(e->cfg.device));
+  RC(validate_slots(e, B, slots));
+  tone_engine::IoSet& io = legacy_set(e);
+  CK(cudaStreamSynchronize(e->stream));
+  memcpy(io.p_slots, slots, (size_t)B * 4);
+  memcpy(io.p_tokens, tokens, (size_t)B * frames * 4);
+  memcpy(io.p_aux, sil, (size_t)B * frames * 8);
+  if (is_last) memcpy(io.p_last, is_last, B);
+  else memset(io.p_last, 0, B);
+  CK(cudaMemcpyAsync(io.d_slots, io.p_slots, (size_t)B * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(io.d_tokens, io.p_tokens, (size_t)B * frames * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(io.d_aux, io.p_aux, (size_t)B * frames * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(io.d_last, io.p_last, B, cudaMemcpyHostToDevice, e->stream));
+  PhraseArgs pa;
+  pa.slots = io.d_slots;
+  pa.tokens = io.d_tokens;
+  pa.sil = io.d_aux;
+  pa.is_last = io.d_last;
+  pa.st = e->st_ph;
+  pa.ring = e->st_ring;
+  pa.hdr = reinterpret_cast<PhHeader*>(io.d_ph);
+  pa.rec = reinterpret_cast<PhRecord*>(io.d_ph + sizeof(PhHeader));
+  pa.pool = reinterpret_cast<unsigned char*>(io.d_ph + sizeof(PhHeader) + (size_t)B * PH_PER_STREAM * sizeof(PhRecord));
+  pa.B = B;
+  pa.T = frames;
+  pa.max_rec = B * PH_PER_STREAM;
+  pa.pool_cap = B * 2304;
+  KLAUNCH(launch_kernel(ctc_phrase_kernel, dim3(1), dim3(PH_THREADS), 0, e->stream, false, pa));
+  CK(cudaMemcpyAsync(io.p_ph, io.d_ph, e->ph_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  io.B = B;
+  io.busy = false;
+  io.ticket = -1;
+  io.ph_complete = true;
+  io.outputs = TONE_OUT_PHRASES;
   return TONE_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ state wire format
+// ------------------------------------------------------------------------------------------------ state wire formats
 // Flat fp16 order (tone/nn/model.py:259-267): preproc 80 | mhsa (2,30,384) | conv (16,384,30) | len 1 |
-// sub1 (1,10,64) | sub2 (32,8,44) | reduction (384,1).
+// sub1 (1,10,64) | sub2 (32,8,44) | reduction (384,1): gathered / scattered on the device (state_io.cuh), one kernel and
+// one copy per STATE_IO_CHUNK slots.  The phrase-splitter state is not part of the model state and is left untouched.
+extern "C" int tone_export_states(tone_engine* e, int32_t n, const int32_t* slots, uint16_t* out) {
+  if (!e || !slots || !out || n < 0) return fail(TONE_EINVAL, "bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  RC(validate_slots(e, n, slots, false));
+  for (int i0 = 0; i0 < n; i0 += STATE_IO_CHUNK) {
+    const int m = std::min((int)STATE_IO_CHUNK, n - i0);
+    int* d = nullptr;
+    RC(ring_slots(e, m, slots + i0, e->stream, &d));
+    export_state_kernel<<<dim3(m, 24), STATE_IO_THREADS, 0, e->stream>>>(state_pool(e), d, reinterpret_cast<__half*>(e->d_state_io));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->p_state_io, e->d_state_io, (size_t)m * TONE_STATE_SIZE * 2, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(out + (size_t)i0 * TONE_STATE_SIZE, e->p_state_io, (size_t)m * TONE_STATE_SIZE * 2);
+  }
+  return TONE_OK;
+}
+
+extern "C" int tone_import_states(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* in) {
+  if (!e || !slots || !in || n < 0) return fail(TONE_EINVAL, "bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  RC(validate_slots(e, n, slots, false));
+  for (int i0 = 0; i0 < n; i0 += STATE_IO_CHUNK) {
+    const int m = std::min((int)STATE_IO_CHUNK, n - i0);
+    CK(cudaStreamSynchronize(e->stream));   // the pinned staging may still be read by the previous chunk's copy
+    memcpy(e->p_state_io, in + (size_t)i0 * TONE_STATE_SIZE, (size_t)m * TONE_STATE_SIZE * 2);
+    int* d = nullptr;
+    RC(ring_slots(e, m, slots + i0, e->stream, &d));
+    CK(cudaMemcpyAsync(e->d_state_io, e->p_state_io, (size_t)m * TONE_STATE_SIZE * 2, cudaMemcpyHostToDevice, e->stream));
+    import_state_kernel<<<dim3(m, 24), STATE_IO_THREADS, 0, e->stream>>>(state_pool(e), d, reinterpret_cast<const __half*>(e->d_state_io));
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return TONE_OK;
+}
+
+// Three-tensor Triton cache layout (tone/scripts/export.py:293-376): cache_last_time (18,384,30) = [mhsa transposed to
+// (2,384,30) | conv (16,384,30)]; cache_last_channel (32,8,50) = [sub2 (32,8,44) | a (32,8,6) tail holding preproc 80,
+// sub1 640, reduction 384 and zero padding, flattened in that order]; cache_last_chan_len = mhsa_len.
 namespace {
-struct Off {
-  static const int pre = 0, mhsa = 80, conv = mhsa + 2 * 30 * 384, len = conv + 16 * 384 * 30, sub1 = len + 1,
-                   sub2 = sub1 + 640, red = sub2 + 32 * 8 * 44, end = red + 384;
-};
-static_assert(Off::end == TONE_STATE_SIZE, "state layout");
+const int TR_TIME = 18 * 384 * 30, TR_CHAN = 32 * 8 * 50, TR_TPAD = 6;
+void flat_to_triton(const uint16_t* f, uint16_t* tm, uint16_t* ch, int64_t* len) {
+  for (int l = 0; l < 2; ++l)
+    for (int c = 0; c < 384; ++c)
+      for (int t = 0; t < 30; ++t) tm[(l * 384 + c) * 30 + t] = f[st_off::mhsa + (l * 30 + t) * 384 + c];
+  memcpy(tm + 2 * 384 * 30, f + st_off::conv, (size_t)16 * 384 * 30 * 2);
+  uint16_t tail[32 * 8 * TR_TPAD];
+  memset(tail, 0, sizeof(tail));
+  memcpy(tail, f + st_off::pre, 80 * 2);
+  memcpy(tail + 80, f + st_off::sub1, 640 * 2);
+  memcpy(tail + 720, f + st_off::red, 384 * 2);
+  for (int cr = 0; cr < 32 * 8; ++cr) {
+    memcpy(ch + cr * 50, f + st_off::sub2 + cr * 44, 44 * 2);
+    memcpy(ch + cr * 50 + 44, tail + cr * TR_TPAD, TR_TPAD * 2);
+  }
+  *len = (int64_t)lrintf(h2f(f[st_off::len]));
+}
+void triton_to_flat(const uint16_t* tm, const uint16_t* ch, int64_t len, uint16_t* f) {
+  for (int l = 0; l < 2; ++l)
+    for (int c = 0; c < 384; ++c)
+      for (int t = 0; t < 30; ++t) f[st_off::mhsa + (l * 30 + t) * 384 + c] = tm[(l * 384 + c) * 30 + t];
+  memcpy(f + st_off::conv, tm + 2 * 384 * 30, (size_t)16 * 384 * 30 * 2);
+  uint16_t tail[32 * 8 * TR_TPAD];
+  for (int cr = 0; cr < 32 * 8; ++cr) {
+    memcpy(f + st_off::sub2 + cr * 44, ch + cr * 50, 44 * 2);
+    memcpy(tail + cr * TR_TPAD, ch + cr * 50 + 44, TR_TPAD * 2);
+  }
+  memcpy(f + st_off::pre, tail, 80 * 2);
+  memcpy(f + st_off::sub1, tail + 80, 640 * 2);
+  memcpy(f + st_off::red, tail + 720, 384 * 2);
+  f[st_off::len] = f2h((float)len);
+}
 }  // namespace
 
-extern "C" int tone_export_state(tone_engine* e, int32_t slot, uint16_t* out) {
-  if (!e || !out) return fail(TONE_EINVAL, "null argument");
-  if (slot < 0 || slot >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slot);
-  CK(cudaSetDevice(e->cfg.device));
-  CK(cudaStreamSynchronize(e->stream));
-  const size_t s = slot;
-  const int F = e->F, T = e->T, T2 = e->T2;
-  std::vector<uint16_t> pre(HOP), feat(SUB1_ROWS * N_MELS), x1((size_t)SUB2_ROWS * X1_ROW), k14(15 * D_MODEL),
-      k15(30 * D_MODEL), conv((size_t)N_LAYERS * CONV_S * D_MODEL);
-  std::vector<float> red(D_MODEL);
-  int len = 0;
-  CK(cudaMemcpy(pre.data(), e->st_pre + s * HOP, HOP * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(feat.data(), e->st_feat + (s * FEAT_ROWS_MAX + F) * N_MELS, feat.size() * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(x1.data(), e->st_x1 + (s * X1_ROWS_MAX + F) * X1_ROW, x1.size() * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(k14.data(), e->st_kv14 + (s * KV_ROWS_MAX + T2) * D_MODEL, k14.size() * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(k15.data(), e->st_kv15 + (s * KV_ROWS_MAX + T) * D_MODEL, k15.size() * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(conv.data(), e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, conv.size() * 2, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(red.data(), e->st_red + s * D_MODEL, D_MODEL * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&len, e->st_len + s, 4, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < HOP; ++i) out[Off::pre + i] = pre[i];
-  for (int r = 0; r < 30; ++r)
-    for (int c = 0; c < D_MODEL; ++c) {
-      out[Off::mhsa + r * D_MODEL + c] = r < 15 ? 0 : f2h(bf2f(k14[(size_t)(r - 15) * D_MODEL + c]));
-      out[Off::mhsa + (30 + r) * D_MODEL + c] = f2h(bf2f(k15[(size_t)r * D_MODEL + c]));
-    }
-  for (int l = 0; l < N_LAYERS; ++l)
-    for (int c = 0; c < D_MODEL; ++c)
-      for (int t = 0; t < CONV_S; ++t)
-        out[Off::conv + ((size_t)l * D_MODEL + c) * CONV_S + t] = f2h(bf2f(conv[((size_t)l * CONV_S + t) * D_MODEL + c]));
-  out[Off::len] = f2h((float)len);
-  for (int i = 0; i < SUB1_ROWS * N_MELS; ++i) out[Off::sub1 + i] = f2h(bf2f(feat[i]));
-  for (int c = 0; c < 32; ++c)
-    for (int r = 0; r < SUB2_ROWS; ++r)
-      for (int f = 0; f < 44; ++f)
-        out[Off::sub2 + (c * SUB2_ROWS + r) * 44 + f] = f2h(bf2f(x1[(size_t)r * X1_ROW + f * 32 + c]));
-  for (int c = 0; c < D_MODEL; ++c) out[Off::red + c] = f2h(red[c]);
+extern "C" int tone_export_states_triton(tone_engine* e, int32_t n, const int32_t* slots, uint16_t* cache_last_time,
+                                         uint16_t* cache_last_channel, int64_t* cache_last_chan_len) {
+  if (!e || !slots || !cache_last_time || !cache_last_channel || !cache_last_chan_len || n < 0)
+    return fail(TONE_EINVAL, "bad argument");
+  std::vector<uint16_t> flat((size_t)TONE_STATE_SIZE);
+  for (int i = 0; i < n; ++i) {
+    RC(tone_export_states(e, 1, slots + i, flat.data()));
+    flat_to_triton(flat.data(), cache_last_time + (size_t)i * TR_TIME, cache_last_channel + (size_t)i * TR_CHAN,
+                   cache_last_chan_len + i);
+  }
   return TONE_OK;
 }
 
-extern "C" int tone_import_state(tone_engine* e, int32_t slot, const uint16_t* in) {
-  if (!e || !in) return fail(TONE_EINVAL, "null argument");
-  if (slot < 0 || slot >= e->cfg.max_slots) return fail(TONE_EINVAL, "slot %d out of range", slot);
-  CK(cudaSetDevice(e->cfg.device));
-  CK(cudaStreamSynchronize(e->stream));
-  const size_t s = slot;
-  const int F = e->F, T = e->T, T2 = e->T2;
-  std::vector<uint16_t> pre(HOP), feat(SUB1_ROWS * N_MELS), x1((size_t)SUB2_ROWS * X1_ROW), k14(15 * D_MODEL),
-      k15(30 * D_MODEL), conv((size_t)N_LAYERS * CONV_S * D_MODEL);
-  std::vector<float> red(D_MODEL);
-  for (int i = 0; i < HOP; ++i) pre[i] = in[Off::pre + i];
-  for (int r = 0; r < 30; ++r)
-    for (int c = 0; c < D_MODEL; ++c) {
-      if (r >= 15) k14[(size_t)(r - 15) * D_MODEL + c] = f2bf(h2f(in[Off::mhsa + r * D_MODEL + c]));
-      k15[(size_t)r * D_MODEL + c] = f2bf(h2f(in[Off::mhsa + (30 + r) * D_MODEL + c]));
-    }
-  for (int l = 0; l < N_LAYERS; ++l)
-    for (int c = 0; c < D_MODEL; ++c)
-      for (int t = 0; t < CONV_S; ++t)
-        conv[((size_t)l * CONV_S + t) * D_MODEL + c] = f2bf(h2f(in[Off::conv + ((size_t)l * D_MODEL + c) * CONV_S + t]));
-  int len = (int)lrintf(h2f(in[Off::len]));
-  len = std::max(0, std::min(len, MHSA_S));
-  for (int i = 0; i < SUB1_ROWS * N_MELS; ++i) feat[i] = f2bf(h2f(in[Off::sub1 + i]));
-  for (int c = 0; c < 32; ++c)
-    for (int r = 0; r < SUB2_ROWS; ++r)
-      for (int f = 0; f < 44; ++f)
-        x1[(size_t)r * X1_ROW + f * 32 + c] = f2bf(h2f(in[Off::sub2 + (c * SUB2_ROWS + r) * 44 + f]));
-  for (int c = 0; c < D_MODEL; ++c) red[c] = h2f(in[Off::red + c]);
-  CK(cudaMemcpy(e->st_pre + s * HOP, pre.data(), HOP * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_feat + (s * FEAT_ROWS_MAX + F) * N_MELS, feat.data(), feat.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_x1 + (s * X1_ROWS_MAX + F) * X1_ROW, x1.data(), x1.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_kv14 + (s * KV_ROWS_MAX + T2) * D_MODEL, k14.data(), k14.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_kv15 + (s * KV_ROWS_MAX + T) * D_MODEL, k15.data(), k15.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_conv + s * N_LAYERS * CONV_S * D_MODEL, conv.data(), conv.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_red + s * D_MODEL, red.data(), D_MODEL * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(e->st_len + s, &len, 4, cudaMemcpyHostToDevice));
-  CK(cudaDeviceSynchronize());
+extern "C" int tone_import_states_triton(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* cache_last_time,
+                                         const uint16_t* cache_last_channel, const int64_t* cache_last_chan_len) {
+  if (!e || !slots || !cache_last_time || !cache_last_channel || !cache_last_chan_len || n < 0)
+    return fail(TONE_EINVAL, "bad argument");
+  std::vector<uint16_t> flat((size_t)TONE_STATE_SIZE);
+  for (int i = 0; i < n; ++i) {
+    triton_to_flat(cache_last_time + (size_t)i * TR_TIME, cache_last_channel + (size_t)i * TR_CHAN, cache_last_chan_len[i],
+                   flat.data());
+    RC(tone_import_states(e, 1, slots + i, flat.data()));
+  }
   return TONE_OK;
 }
 

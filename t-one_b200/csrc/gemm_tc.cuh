@@ -34,8 +34,6 @@ enum GemmKind : int {
                     // the slices in fp32 in a fixed order)
   G_VATT = 10,      // score-sharing attention layers in one kernel: v = acc + b for one head (BN = 48) of whole streams,
                     // then ctx bf16 = P v with the probabilities P published by the last recompute layer
-  G_GLU_DW = 9,     // conv module in one kernel: GLU epilogue, then the causal depthwise conv k=31 + BN + SiLU over
-                    // [30-row cache | T new rows] per stream and channel, cache roll included (tiles hold whole streams)
 };
 
 struct GemmArgs {
@@ -64,11 +62,6 @@ struct GemmArgs {
   int ss_ld;                  // floats per row of ss (= number of N tiles of the producer)
   const float* ss;            // consumer side: nullable
   int ss_tiles;
-  // G_GLU_DW: depthwise stage
-  bf16* dw_cache;             // [slots][16][30][384], layer offset applied
-  long long dw_cache_stride;  // elements between slots
-  const float* dw_w;          // [31][384] BN-folded taps
-  const float* dw_b;          // [384]
   // Raw operand views, used only by the SIMT debug kernels (gemm_ref.cuh); the tensor-core path reads through
   // the tensor maps.
   const bf16* A;
@@ -82,7 +75,7 @@ template <int KIND>
 struct KindTraits {
   static constexpr bool gather = (KIND == G_CONV0 || KIND == G_CONV1 || KIND == G_KV);
   // rows of a tile are G whole streams x R frames (gather kinds, and dense kinds that need whole streams per tile)
-  static constexpr bool stream_rows = gather || (KIND == G_GLU_DW) || (KIND == G_VATT);
+  static constexpr bool stream_rows = gather || (KIND == G_VATT);
 };
 
 // DEEP = one CTA per SM with the whole shared memory as the operand ring: the small-batch GEMMs of this model are
@@ -93,8 +86,8 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGES = DEEP ? (200 * 1024) / (A_BYTES + B_BYTES) : ((BN > 64) ? 3 : 4);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  // + barriers (256) + per-column constants (1 KB) + depthwise taps of G_GLU_DW (33 x 32 floats) + alignment slack
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024 + 4352 + 1024;
+  // + barriers (256) + per-column constants (1 KB) + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024 + 1024;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogues
@@ -141,14 +134,6 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
     }
   } else if constexpr (KIND == G_DECODER) {
     if (t < 48) s_c0[t] = t < 35 ? __ldg(a.bias + t) : 0.f;
-  } else if constexpr (KIND == G_GLU_DW) {
-    if (t < BN) s_c0[t] = __ldg(a.bias + n0 + t);
-    // depthwise taps [31][32] + bias [32] of this tile's 32 channels, behind the per-column constants
-    float* wS = s_c1 + 128;
-    for (int i = t; i < 32 * 32; i += EPI_THREADS) {
-      const int j = i >> 5, c = i & 31;
-      wS[i] = (j < 31) ? __ldg(a.dw_w + j * 384 + blockIdx.y * 32 + c) : __ldg(a.dw_b + blockIdx.y * 32 + c);
-    }
   } else {
     if (t < BN) s_c0[t] = a.bias ? __ldg(a.bias + n0 + t) : 0.f;
   }
@@ -158,7 +143,7 @@ __device__ __forceinline__ void stage_constants(const GemmArgs& a, float* s_c0, 
 template <int KIND, int BN>
 struct OutCfg {
   static constexpr bool f32 = (KIND == G_STORE_F32 || KIND == G_KV || KIND == G_RESID);
-  static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU || KIND == G_GLU_DW) ? BN : BN * 2);
+  static constexpr int ROW_BYTES = f32 ? BN * 4 : ((KIND == G_SWIGLU || KIND == G_GLU) ? BN : BN * 2);
   static constexpr int STRIDE = ROW_BYTES + 16;   // +16 B: float4 stores of a quarter-warp hit distinct banks
   static constexpr int LPR = ROW_BYTES / 16;      // lanes per output row in the coalesced phase
   static constexpr int RPI = 32 / LPR;            // rows per warp instruction
@@ -297,97 +282,6 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
                                                   pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
     }
-    return;
-  } else if constexpr (KIND == G_GLU_DW) {
-    // experimental fused conv module (off by default): one warp per quarter does all columns, then the depthwise stage
-    const int n0_out = blockIdx.y * (BN / 2);
-    float rs = 1.f;
-    if (a.ss) {
-      const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
-      if (rme.valid) {
-        const float* sp = a.ss + rme.out_row * a.ss_ld;
-        float t = 0.f;
-        for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
-        rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
-      }
-    }
-    float dwc[3][30];
-    if (!hf) {
-#pragma unroll
-      for (int si = 0; si < 3; ++si) {
-        const int g = q + 4 * si, b = blockIdx.x * a.G + g;
-        if (g < a.G && b < a.M) {
-          const bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + blockIdx.y * 32 + lane;
-#pragma unroll
-          for (int i = 0; i < 30; ++i) dwc[si][i] = __bfloat162float(cache[i * 384]);
-        }
-      }
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    if (!hf) {
-      float acc[BN];
-      tmem_load_row<BN>(tmem_row_base, acc);
-      const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
-      const uint32_t c0a = smem_u32(s_c0);
-      constexpr int HW = BN / 2;
-#pragma unroll
-      for (int c = 0; c < HW; c += 8) {
-        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
-        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
-        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        float r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = fmaf(acc[c + i], rs, gb[i]) * sigmoid_f(fmaf(acc[HW + c + i], rs, ub[i]));
-        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                                         pack_bf16x2(r[6], r[7])));
-      }
-    }
-    bar_epilogue();   // the whole GLU tile is staged
-    if (hf) return;
-    static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
-    const int T = a.R;
-    const int cg = blockIdx.y * 32 + lane;            // global channel
-    const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
-    const float bias = wS[31 * 32 + lane];
-#pragma unroll
-    for (int si = 0; si < 3; ++si) {
-      const int g = q + 4 * si, b = blockIdx.x * a.G + g;
-      if (g < a.G && b < a.M) {
-        bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
-        float col[30 + 13];
-#pragma unroll
-        for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
-#pragma unroll
-        for (int t = 0; t < 13; ++t)
-          if (t < T)
-            col[30 + t] = __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
-        float acc2[13];
-#pragma unroll
-        for (int t = 0; t < 13; ++t) acc2[t] = bias;
-#pragma unroll
-        for (int j = 0; j < 31; ++j) {
-          const float wj = wS[j * 32 + lane];
-#pragma unroll
-          for (int t = 0; t < 13; ++t)
-            if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
-        }
-        bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
-#pragma unroll
-        for (int t = 0; t < 13; ++t)
-          if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
-#pragma unroll
-        for (int i = 0; i < 30; ++i) {
-          float vsel = col[i];
-#pragma unroll
-          for (int t = 1; t <= 13; ++t)
-            if (t == T) vsel = col[i + t];
-          cache[i * 384] = __float2bfloat16(vsel);
-        }
-      }
-    }
-    (void)n0_out;
     return;
   } else {
     constexpr bool gated = (KIND == G_SWIGLU || KIND == G_GLU);
@@ -706,97 +600,6 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
                                                   pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
     }
     return;
-  } else if constexpr (KIND == G_GLU_DW) {
-    // experimental fused conv module (off by default): one warp per quarter does all columns, then the depthwise stage
-    const int n0_out = ty * (BN / 2);
-    float rs = 1.f;
-    if (a.ss) {
-      const RowInfo rme = row_info_p<KIND, PERSIST>(a, tx, q * 32 + lane);
-      if (rme.valid) {
-        const float* sp = a.ss + rme.out_row * a.ss_ld;
-        float t = 0.f;
-        for (int k = 0; k < a.ss_tiles; ++k) t += sp[k];
-        rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
-      }
-    }
-    float dwc[3][30];
-    if (!hf) {
-#pragma unroll
-      for (int si = 0; si < 3; ++si) {
-        const int g = q + 4 * si, b = tx * a.G + g;
-        if (g < a.G && b < a.M) {
-          const bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + ty * 32 + lane;
-#pragma unroll
-          for (int i = 0; i < 30; ++i) dwc[si][i] = __bfloat162float(cache[i * 384]);
-        }
-      }
-    }
-    mbar_wait(tmem_full, par);
-    tc_fence_after();
-    if (!hf) {
-      float acc[BN];
-      tmem_load_row<BN>(tmem_row_base, acc);
-      const uint32_t srow = smem_u32(stage) + (q * 32 + lane) * O::STRIDE;
-      const uint32_t c0a = smem_u32(s_c0);
-      constexpr int HW = BN / 2;
-#pragma unroll
-      for (int c = 0; c < HW; c += 8) {
-        const float4 g0 = lds128(c0a + c * 4), g1 = lds128(c0a + c * 4 + 16);
-        const float4 u0 = lds128(c0a + (HW + c) * 4), u1 = lds128(c0a + (HW + c) * 4 + 16);
-        const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float ub[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        float r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = fmaf(acc[c + i], rs, gb[i]) * sigmoid_f(fmaf(acc[HW + c + i], rs, ub[i]));
-        sts128u(srow + c * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                                         pack_bf16x2(r[6], r[7])));
-      }
-    }
-    bar_epilogue_p(bar_id);   // the whole GLU tile is staged
-    if (hf) return;
-    static_assert(KIND != G_GLU_DW || BN == 64, "one lane per output channel");   // and a.G <= 12: 3 streams per warp
-    const int T = a.R;
-    const int cg = ty * 32 + lane;            // global channel
-    const float* wS = s_c1 + 128;                     // [31][32] taps + [32] bias staged by stage_constants
-    const float bias = wS[31 * 32 + lane];
-#pragma unroll
-    for (int si = 0; si < 3; ++si) {
-      const int g = q + 4 * si, b = tx * a.G + g;
-      if (g < a.G && b < a.M) {
-        bf16* cache = a.dw_cache + (long long)a.slots[b] * a.dw_cache_stride + cg;
-        float col[30 + 13];
-#pragma unroll
-        for (int i = 0; i < 30; ++i) col[i] = dwc[si][i];
-#pragma unroll
-        for (int t = 0; t < 13; ++t)
-          if (t < T)
-            col[30 + t] = __bfloat162float(*reinterpret_cast<const bf16*>(stage + (g * T + t) * O::STRIDE + lane * 2));
-        float acc2[13];
-#pragma unroll
-        for (int t = 0; t < 13; ++t) acc2[t] = bias;
-#pragma unroll
-        for (int j = 0; j < 31; ++j) {
-          const float wj = wS[j * 32 + lane];
-#pragma unroll
-          for (int t = 0; t < 13; ++t)
-            if (t < T) acc2[t] = fmaf(wj, col[t + j], acc2[t]);
-        }
-        bf16* eo = reinterpret_cast<bf16*>(a.out) + ((long long)b * T) * a.ldo + cg;
-#pragma unroll
-        for (int t = 0; t < 13; ++t)
-          if (t < T) eo[(long long)t * a.ldo] = __float2bfloat16(silu_f(acc2[t]));
-#pragma unroll
-        for (int i = 0; i < 30; ++i) {
-          float vsel = col[i];
-#pragma unroll
-          for (int t = 1; t <= 13; ++t)
-            if (t == T) vsel = col[i + t];
-          cache[i * 384] = __float2bfloat16(vsel);
-        }
-      }
-    }
-    (void)n0_out;
-    return;
   } else {
     constexpr bool gated = (KIND == G_SWIGLU || KIND == G_GLU);
     // element offset of this tile's first output column
@@ -1065,7 +868,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, DEEP ? 1 : 2) gemm_tc_kernel(con
             tma_load_3d(dA + g * a.R * 128, &tmA, &full[s], it * 64, 0, a.slots[blockIdx.x * a.G + g]);
       } else {
         tma_load_2d(dA, &tmA, &full[s], kz + it * 64,
-                    (KIND == G_GLU_DW || KIND == G_VATT) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
+                    (KIND == G_VATT) ? blockIdx.x * a.G * a.R : blockIdx.x * 128);
       }
     };
     if (lane < npre) load_a(lane, lane);

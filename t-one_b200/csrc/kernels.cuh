@@ -32,7 +32,8 @@ constexpr int MAX_T = 13;
 // ------------------------------------------------------------------------------------------------ begin step
 struct BeginArgs {
   const int* slots;          // [B]
-  const int* pcm;            // [B][C] int32
+  const void* pcm;           // [B][C] int32 or int16 samples (pcm_fmt: 0 | 1), int16 range
+  int pcm_fmt;
   const __half* feats_in;    // nullable: feature-input mode (reference skip_preprocessor=True, tone/nn/model.py:151-160):
                              // [B][64][F] fp16 log-mel features replace the waveform front end; `pre` is left untouched
   __half* pre;               // [slots][80] last samples of the previous chunk (fp16-exact values)
@@ -137,12 +138,14 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     }
     // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
     __half* pre = a.pre + (size_t)slot * HOP;
-    const int* pcm = a.pcm + (size_t)b * C;
+    const int* pcm32 = reinterpret_cast<const int*>(a.pcm) + (size_t)b * C;
+    const short* pcm16 = reinterpret_cast<const short*>(a.pcm) + (size_t)b * C;
     if (!a.feats_in) {
       for (int i = tid; i < UH; i += BEGIN_THREADS) {
         __half v = __float2half_rn(0.f);
         if (i < HOP) v = pre[i];
-        else if (i < C + HOP) v = __float2half_rn(static_cast<float>(pcm[i - HOP]) / 32767.0f);
+        else if (i < C + HOP)
+          v = __float2half_rn(static_cast<float>(a.pcm_fmt ? (int)pcm16[i - HOP] : pcm32[i - HOP]) / 32767.0f);
         uh[i] = v;
       }
     }

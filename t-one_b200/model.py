@@ -22,28 +22,43 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TONE_B200_LIB") or os.path.join(_HERE, "libtone_b200.so")
 
 TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1, -2, -3, -4, -5
+PCM_I32, PCM_I16 = 0, 1
+OUT_LOGPROBS, OUT_TOKENS, OUT_SIL, OUT_PHRASES = 1, 2, 4, 8
+FLAG_NO_PDL, FLAG_NO_FUSED_VATT = 1, 2
 
 # every symbol include/tone_b200.h declares
 SYMBOLS = (
     "tone_create", "tone_destroy", "tone_get_info", "tone_last_error", "tone_load_weight",
     "tone_finalize_weights", "tone_alloc_slots", "tone_release_slots", "tone_reset_slots", "tone_step",
-    "tone_stage", "tone_step_staged", "tone_fetch", "tone_fetch_greedy", "tone_sync", "tone_step_device", "tone_host_buffers", "tone_export_state",
-    "tone_import_state", "tone_step_debug", "tone_selftest_gemm", "tone_cluster_prof_read", "tone_step_features",
+    "tone_submit", "tone_wait", "tone_next_staging", "tone_ticket_phrases", "tone_step_features",
+    "tone_stage", "tone_step_staged", "tone_fetch", "tone_sync", "tone_fetch_greedy", "tone_step_device",
+    "tone_export_states", "tone_import_states", "tone_export_states_triton", "tone_import_states_triton",
+    "tone_step_debug", "tone_selftest_gemm", "tone_selftest_phrases",
 )
 
 
 class ToneConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_samples", C.c_int32), ("max_slots", C.c_int32),
                 ("max_batch", C.c_int32), ("gemm_impl", C.c_int32), ("use_graph", C.c_int32),
-                ("cluster_max_batch", C.c_int32)]
+                ("lanes", C.c_int32), ("lane_min_batch", C.c_int32), ("persist_min_tiles", C.c_int32),
+                ("persist_mode", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32)]
 
 
 class ToneInfo(C.Structure):
     _fields_ = [("chunk_samples", C.c_int32), ("frames_out", C.c_int32), ("n_classes", C.c_int32),
                 ("state_size", C.c_int32), ("max_slots", C.c_int32), ("max_batch", C.c_int32),
                 ("launches_per_step", C.c_int32), ("n_taps", C.c_int32),
-                ("state_bytes_per_slot", C.c_int64), ("weight_bytes", C.c_int64)]
+                ("state_bytes_per_slot", C.c_int64), ("weight_bytes", C.c_int64),
+                ("pipeline_depth", C.c_int32), ("max_phrases_per_step", C.c_int32)]
 
+
+class TonePhrase(C.Structure):
+    _fields_ = [("batch_index", C.c_int32), ("start_frame", C.c_int32), ("end_frame", C.c_int32),
+                ("text_offset", C.c_int32), ("text_len", C.c_int32)]
+
+
+PHRASE_DTYPE = np.dtype([("batch_index", "<i4"), ("start_frame", "<i4"), ("end_frame", "<i4"),
+                         ("text_offset", "<i4"), ("text_len", "<i4")])
 
 _lib = None
 
@@ -60,29 +75,37 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
             "(needs nvcc); there is no CPU fallback for the acoustic-model step.")
     lib = C.CDLL(p)
     vp, i32p, f32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    u8p, u16p, i16p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_int16), C.POINTER(C.c_int64)
     lib.tone_create.argtypes = [C.POINTER(ToneConfig), C.POINTER(vp)]
     lib.tone_destroy.argtypes = [vp]
     lib.tone_destroy.restype = None
     lib.tone_get_info.argtypes = [vp, C.POINTER(ToneInfo)]
     lib.tone_last_error.argtypes = []
     lib.tone_last_error.restype = C.c_char_p
-    lib.tone_load_weight.argtypes = [vp, C.c_char_p, f32p, C.POINTER(C.c_int64), C.c_int32]
+    lib.tone_load_weight.argtypes = [vp, C.c_char_p, f32p, i64p, C.c_int32]
     lib.tone_finalize_weights.argtypes = [vp]
     lib.tone_alloc_slots.argtypes = [vp, C.c_int32, i32p]
     lib.tone_release_slots.argtypes = [vp, C.c_int32, i32p]
     lib.tone_reset_slots.argtypes = [vp, C.c_int32, i32p]
     lib.tone_step.argtypes = [vp, C.c_int32, i32p, i32p, f32p, i32p]
+    lib.tone_submit.argtypes = [vp, C.c_int32, i32p, vp, C.c_int32, u8p, C.c_int32, i32p]
+    lib.tone_wait.argtypes = [vp, C.c_int32, f32p, i32p, f32p]
+    lib.tone_next_staging.argtypes = [vp, C.POINTER(i32p), C.POINTER(i16p), C.POINTER(u8p)]
+    lib.tone_ticket_phrases.argtypes = [vp, C.c_int32, C.POINTER(C.POINTER(TonePhrase)), i32p, C.POINTER(u8p), i32p]
+    lib.tone_step_features.argtypes = [vp, C.c_int32, i32p, vp, f32p, i32p]
     lib.tone_stage.argtypes = [vp, C.c_int32, i32p, i32p]
     lib.tone_step_staged.argtypes = [vp, C.c_int32, vp]
     lib.tone_fetch.argtypes = [vp, C.c_int32, f32p, i32p]
     lib.tone_sync.argtypes = [vp]
     lib.tone_fetch_greedy.argtypes = [vp, C.c_int32, i32p, f32p]
-    lib.tone_step_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
-    lib.tone_host_buffers.argtypes = [vp, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f32p), C.POINTER(i32p)]
-    lib.tone_export_state.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
-    lib.tone_import_state.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
+    lib.tone_step_device.argtypes = [vp, C.c_int32, i32p, vp, C.c_int32, vp, vp, vp]
+    lib.tone_export_states.argtypes = [vp, C.c_int32, i32p, u16p]
+    lib.tone_import_states.argtypes = [vp, C.c_int32, i32p, u16p]
+    lib.tone_export_states_triton.argtypes = [vp, C.c_int32, i32p, u16p, u16p, i64p]
+    lib.tone_import_states_triton.argtypes = [vp, C.c_int32, i32p, u16p, u16p, i64p]
     lib.tone_step_debug.argtypes = [vp, C.c_int32, i32p, i32p, f32p, i32p, f32p]
     lib.tone_selftest_gemm.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_int32]
+    lib.tone_selftest_phrases.argtypes = [vp, C.c_int32, i32p, C.c_int32, i32p, f32p, u8p]
     for s in SYMBOLS:
         if s not in ("tone_destroy", "tone_last_error"):
             getattr(lib, s).restype = C.c_int
@@ -112,15 +135,32 @@ def _f32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _u16p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+class Ticket:
+    """One pipelined step in flight (``Engine.submit``): what ``Engine.wait`` needs to shape its results."""
+    __slots__ = ("id", "B", "outputs")
+
+    def __init__(self, id_: int, B: int, outputs: int):
+        self.id, self.B, self.outputs = id_, B, outputs
+
+
 class Engine:
     """One engine per GPU: weights, resident stream slots, step."""
 
     def __init__(self, weights=None, chunk_samples: int = 2400, max_slots: int = 64, max_batch: Optional[int] = None,
-                 device: int = 0, gemm_impl: int = 0, use_graph: bool = True, cluster_max_batch: int = 0):
+                 device: int = 0, gemm_impl: int = 0, use_graph: bool = True, *, lanes: int = 0, lane_min_batch: int = 0,
+                 persist_min_tiles: int = 0, persist_mode: int = 0, split_k: int = 0, flags: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph),
-                         int(cluster_max_batch))
+                         lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags)
         rc = self._lib.tone_create(C.byref(cfg), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()
@@ -129,7 +169,6 @@ class Engine:
         self.info = self._get_info()
         self.T = self.info.frames_out
         self.chunk_samples = chunk_samples
-        self._wrap_host_buffers()
         if weights is not None:
             self.load_weights(weights)
 
@@ -142,16 +181,6 @@ class Engine:
         info = ToneInfo()
         self._ck(self._lib.tone_get_info(self._h, C.byref(info)))
         return info
-
-    def _wrap_host_buffers(self):
-        i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
-        s, p, l, t = i32p(), i32p(), f32p(), i32p()
-        self._ck(self._lib.tone_host_buffers(self._h, C.byref(s), C.byref(p), C.byref(l), C.byref(t)))
-        mb = self.info.max_batch
-        self.h_slots = np.ctypeslib.as_array(s, shape=(mb,))
-        self.h_pcm = np.ctypeslib.as_array(p, shape=(mb, self.chunk_samples))
-        self.h_logprobs = np.ctypeslib.as_array(l, shape=(mb, 13, 35)).reshape(-1)
-        self.h_tokens = np.ctypeslib.as_array(t, shape=(mb, 13)).reshape(-1)
 
     def close(self):
         self._finalizer()
@@ -194,6 +223,79 @@ class Engine:
         self._ck(self._lib.tone_step(self._h, B, _i32p(s), _i32p(x), _f32p(lp), _i32p(tk) if want_tokens else None))
         return lp, tk
 
+    # pipelined form: up to info.pipeline_depth tickets in flight; copies of neighbouring steps overlap the kernels
+    def next_staging(self, B: int):
+        """Pinned staging of the set the next ``submit`` uses: (slots int32 (B,), pcm int16 (B, chunk), is_last uint8 (B,)).
+        Fill them in place and call ``submit_staged`` - no intermediate host copy."""
+        sp, pp, lp = C.POINTER(C.c_int32)(), C.POINTER(C.c_int16)(), C.POINTER(C.c_uint8)()
+        self._ck(self._lib.tone_next_staging(self._h, C.byref(sp), C.byref(pp), C.byref(lp)))
+        return (np.ctypeslib.as_array(sp, shape=(B,)), np.ctypeslib.as_array(pp, shape=(B, self.chunk_samples)),
+                np.ctypeslib.as_array(lp, shape=(B,)))
+
+    def submit(self, slots, pcm, outputs: int = OUT_LOGPROBS | OUT_TOKENS, is_last=None) -> Ticket:
+        """Enqueue one step (asynchronous).  pcm int16 or int32 (B, chunk); is_last uint8/bool (B,) for OUT_PHRASES."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        x = np.ascontiguousarray(pcm)
+        B = len(s)
+        if x.dtype not in (np.int16, np.int32) or x.shape != (B, self.chunk_samples):
+            raise ValueError(f"pcm must be int16/int32 ({B}, {self.chunk_samples}), got {x.dtype} {x.shape}")
+        last = None if is_last is None else np.ascontiguousarray(is_last, dtype=np.uint8)
+        if last is not None and last.shape != (B,):
+            raise ValueError(f"is_last must have shape ({B},)")
+        t = C.c_int32(-1)
+        self._ck(self._lib.tone_submit(self._h, B, _i32p(s), x.ctypes.data_as(C.c_void_p),
+                                       PCM_I16 if x.dtype == np.int16 else PCM_I32,
+                                       _u8p(last) if last is not None else None, outputs, C.byref(t)))
+        return Ticket(t.value, B, outputs)
+
+    def wait(self, ticket: Ticket) -> dict:
+        """Block until the ticket's outputs are on the host -> dict with the requested of 'logprobs' (B,T,35),
+        'tokens' (B,T), 'sil' (B,T,2), 'phrases' (list of (batch_index, start_frame, end_frame, label_ids))."""
+        B, o = ticket.B, ticket.outputs
+        lp = np.empty((B, self.T, 35), dtype=np.float32) if o & OUT_LOGPROBS else None
+        tk = np.empty((B, self.T), dtype=np.int32) if o & OUT_TOKENS else None
+        sl = np.empty((B, self.T, 2), dtype=np.float32) if o & OUT_SIL else None
+        self._ck(self._lib.tone_wait(self._h, ticket.id, _f32p(lp) if lp is not None else None,
+                                     _i32p(tk) if tk is not None else None, _f32p(sl) if sl is not None else None))
+        out = {}
+        if lp is not None:
+            out["logprobs"] = lp
+        if tk is not None:
+            out["tokens"] = tk
+        if sl is not None:
+            out["sil"] = sl
+        if o & OUT_PHRASES:
+            out["phrases"] = self.ticket_phrases(ticket.id)
+        return out
+
+    def ticket_phrases(self, ticket_id: int):
+        """Finished phrases of a waited ticket: list of (batch_index, start_frame, end_frame, label ids uint8 array)."""
+        ph, n = C.POINTER(TonePhrase)(), C.c_int32()
+        pool, npool = C.POINTER(C.c_uint8)(), C.c_int32()
+        self._ck(self._lib.tone_ticket_phrases(self._h, ticket_id, C.byref(ph), C.byref(n), C.byref(pool), C.byref(npool)))
+        if n.value == 0:
+            return []
+        rec = np.frombuffer((C.c_char * (n.value * C.sizeof(TonePhrase))).from_address(C.addressof(ph.contents)),
+                            dtype=PHRASE_DTYPE).copy()
+        text = np.ctypeslib.as_array(pool, shape=(max(npool.value, 1),)).copy()
+        return [(int(r["batch_index"]), int(r["start_frame"]), int(r["end_frame"]),
+                 text[r["text_offset"]: r["text_offset"] + r["text_len"]]) for r in rec]
+
+    def step_phrases(self, slots, pcm, is_last=None):
+        """Synchronous step that returns only the phrases finished by this chunk (device-side splitter + greedy decode)."""
+        return self.wait(self.submit(slots, pcm, OUT_PHRASES, is_last))["phrases"]
+
+    def selftest_phrases(self, slots, tokens, sil, is_last=None):
+        """Debug: the device-side splitter alone on per-frame (tokens (B,n), sil (B,n,2)), n <= 13 frames per call."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        tk = np.ascontiguousarray(tokens, dtype=np.int32)
+        sl = np.ascontiguousarray(sil, dtype=np.float32)
+        B, n = tk.shape
+        last = None if is_last is None else np.ascontiguousarray(is_last, dtype=np.uint8)
+        self._ck(self._lib.tone_selftest_phrases(self._h, B, _i32p(s), n, _i32p(tk), _f32p(sl),
+                                                 _u8p(last) if last is not None else None))
+        return self.ticket_phrases(-1)
+
     def step_features(self, slots, feats, want_tokens: bool = True):
         """Feature-input mode (reference ``skip_preprocessor=True``): feats (B, 64, F) log-mel, rounded to fp16."""
         s = np.ascontiguousarray(slots, dtype=np.int32)
@@ -216,61 +318,84 @@ class Engine:
         self._ck(self._lib.tone_step_debug(self._h, B, _i32p(s), _i32p(x), _f32p(lp), _i32p(tk), _f32p(taps)))
         return lp, tk, taps
 
-    # zero-copy staged API (benchmarks): write self.h_slots / self.h_pcm, then stage(), step_staged(), fetch()
-    def stage(self, B: int) -> None:
-        self._ck(self._lib.tone_stage(self._h, B, _i32p(self.h_slots), _i32p(self.h_pcm)))
+    # staged API: stage once, step any number of times on the staged chunk, fetch
+    def stage(self, slots, pcm) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        x = np.ascontiguousarray(pcm, dtype=np.int32)
+        self._ck(self._lib.tone_stage(self._h, len(s), _i32p(s), _i32p(x)))
 
     def step_staged(self, B: int, cuda_stream: int = 0) -> None:
         self._ck(self._lib.tone_step_staged(self._h, B, C.c_void_p(cuda_stream) if cuda_stream else None))
 
-    def step_device(self, B: int, d_slots: int, d_pcm: int, d_logprobs: int = 0, d_tokens: int = 0,
+    def step_device(self, slots, d_pcm: int, pcm_format: int = PCM_I16, d_logprobs: int = 0, d_tokens: int = 0,
                     cuda_stream: int = 0) -> None:
-        """Asynchronous step on raw device pointers (e.g. torch tensors' data_ptr())."""
+        """Asynchronous step on raw device pointers (e.g. torch tensors' data_ptr()); slot ids are host ints."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
         vp = C.c_void_p
-        self._ck(self._lib.tone_step_device(self._h, B, vp(d_slots or None), vp(d_pcm or None),
+        self._ck(self._lib.tone_step_device(self._h, len(s), _i32p(s), vp(d_pcm or None), pcm_format,
                                             vp(d_logprobs or None), vp(d_tokens or None), vp(cuda_stream or None)))
 
     def fetch(self, B: int, tokens: bool = True):
-        self._ck(self._lib.tone_fetch(self._h, B, _f32p(self.h_logprobs), _i32p(self.h_tokens) if tokens else None))
-        lp = self.h_logprobs[: B * self.T * 35].reshape(B, self.T, 35)
-        tk = self.h_tokens[: B * self.T].reshape(B, self.T)
+        lp = np.empty((B, self.T, 35), dtype=np.float32)
+        tk = np.empty((B, self.T), dtype=np.int32)
+        self._ck(self._lib.tone_fetch(self._h, B, _f32p(lp), _i32p(tk) if tokens else None))
         return lp, tk
 
     def step_greedy(self, slots, pcm):
         """Step and fetch only what greedy decoding needs: tokens int32 (B,T) and the (space, blank) log-probs
         fp32 (B,T,2) that the phrase splitter thresholds on."""
-        s = np.ascontiguousarray(slots, dtype=np.int32)
-        x = np.ascontiguousarray(pcm, dtype=np.int32)
-        B = len(s)
-        if x.shape != (B, self.chunk_samples):
-            raise ValueError(f"pcm must be ({B}, {self.chunk_samples}), got {x.shape}")
-        self._ck(self._lib.tone_stage(self._h, B, _i32p(s), _i32p(x)))
-        self._ck(self._lib.tone_step_staged(self._h, B, None))
-        tk = np.empty((B, self.T), dtype=np.int32)
-        sil = np.empty((B, self.T, 2), dtype=np.float32)
-        self._ck(self._lib.tone_fetch_greedy(self._h, B, _i32p(tk), _f32p(sil)))
-        return tk, sil
-
-    def step_pinned(self, B: int):
-        """H2D of the pinned inputs + step + D2H into the pinned outputs, synchronous (the e2e path)."""
-        self._ck(self._lib.tone_step(self._h, B, _i32p(self.h_slots), _i32p(self.h_pcm), _f32p(self.h_logprobs),
-                                     _i32p(self.h_tokens)))
-        return (self.h_logprobs[: B * self.T * 35].reshape(B, self.T, 35), self.h_tokens[: B * self.T].reshape(B, self.T))
+        r = self.wait(self.submit(slots, pcm, OUT_TOKENS | OUT_SIL))
+        return r["tokens"], r["sil"]
 
     def sync(self) -> None:
         self._ck(self._lib.tone_sync(self._h))
 
-    # -- state wire format
-    def export_state(self, slot: int) -> np.ndarray:
-        out = np.empty(self.info.state_size, dtype=np.float16)
-        self._ck(self._lib.tone_export_state(self._h, int(slot), out.ctypes.data_as(C.POINTER(C.c_uint16))))
+    # -- state wire formats
+    def export_states(self, slots) -> np.ndarray:
+        """-> (n, 219729) float16, the reference's flat state of each slot."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        out = np.empty((len(s), self.info.state_size), dtype=np.float16)
+        self._ck(self._lib.tone_export_states(self._h, len(s), _i32p(s), _u16p(out)))
         return out
+
+    def import_states(self, slots, states) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        a = np.ascontiguousarray(states, dtype=np.float16)
+        if a.shape != (len(s), self.info.state_size):
+            raise ValueError(f"states must be ({len(s)}, {self.info.state_size}), got {a.shape}")
+        self._ck(self._lib.tone_import_states(self._h, len(s), _i32p(s), _u16p(a)))
+
+    def export_state(self, slot: int) -> np.ndarray:
+        return self.export_states([int(slot)])[0]
 
     def import_state(self, slot: int, state: np.ndarray) -> None:
         a = np.ascontiguousarray(state, dtype=np.float16)
         if a.shape != (self.info.state_size,):
             raise ValueError(f"state must be ({self.info.state_size},), got {a.shape}")
-        self._ck(self._lib.tone_import_state(self._h, int(slot), a.ctypes.data_as(C.POINTER(C.c_uint16))))
+        self.import_states([int(slot)], a[None])
+
+    def export_states_triton(self, slots):
+        """-> (cache_last_time (n,18,384,30) f16, cache_last_channel (n,32,8,50) f16, cache_last_chan_len (n,) i64);
+        reference: tone/scripts/export.py:335-376."""
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        n = len(s)
+        tm = np.empty((n, 18, 384, 30), dtype=np.float16)
+        ch = np.empty((n, 32, 8, 50), dtype=np.float16)
+        ln = np.empty((n,), dtype=np.int64)
+        self._ck(self._lib.tone_export_states_triton(self._h, n, _i32p(s), _u16p(tm), _u16p(ch),
+                                                     ln.ctypes.data_as(C.POINTER(C.c_int64))))
+        return tm, ch, ln
+
+    def import_states_triton(self, slots, cache_last_time, cache_last_channel, cache_last_chan_len) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int32)
+        n = len(s)
+        tm = np.ascontiguousarray(cache_last_time, dtype=np.float16)
+        ch = np.ascontiguousarray(cache_last_channel, dtype=np.float16)
+        ln = np.ascontiguousarray(cache_last_chan_len, dtype=np.int64)
+        if tm.shape != (n, 18, 384, 30) or ch.shape != (n, 32, 8, 50) or ln.shape != (n,):
+            raise ValueError("expected cache_last_time (n,18,384,30), cache_last_channel (n,32,8,50), cache_last_chan_len (n,)")
+        self._ck(self._lib.tone_import_states_triton(self._h, n, _i32p(s), _u16p(tm), _u16p(ch),
+                                                     ln.ctypes.data_as(C.POINTER(C.c_int64))))
 
     def selftest_gemm(self, A: np.ndarray, W: np.ndarray, block_n: int = 64) -> np.ndarray:
         A = np.ascontiguousarray(A, dtype=np.float32)
@@ -282,15 +407,12 @@ class Engine:
         return out
 
 
-class StreamSlots:
-    """Opaque model state for the device-resident mode: the slot ids of B streams.
-
-    The pipeline never inspects the model state (reference: tone/pipeline.py:143-147,172; the Triton client's
-    state is a bare counter, dev/triton/client_wer.py:138-207), so a handle is a valid state."""
+class _SlotCore:
+    """Shared by every handle of one group of streams: the slots, their owner and the current generation."""
 
     def __init__(self, engine: Engine, slots: np.ndarray):
-        self.engine, self.slots = engine, slots
-        self._fin = weakref.finalize(self, StreamSlots._release, weakref.ref(engine), slots.copy())
+        self.engine, self.slots, self.gen, self.closed = engine, slots, 0, False
+        self._fin = weakref.finalize(self, _SlotCore._release, weakref.ref(engine), slots.copy())
 
     @staticmethod
     def _release(engine_ref, slots):
@@ -301,11 +423,56 @@ class StreamSlots:
             except Exception:
                 pass
 
-    def release(self):
+    def close(self):
+        self.closed = True
         self._fin()
 
+
+class StreamSlots:
+    """Opaque model state for the device-resident mode: a handle on the slots of B streams.
+
+    The pipeline never inspects the model state (reference: tone/pipeline.py:143-147,172; the Triton client's
+    state is a bare counter, dev/triton/client_wer.py:138-207), so a handle is a valid state.
+
+    Contract (differs from the reference's value semantics, by design): the per-stream state lives in HBM and is
+    advanced IN PLACE by ``forward``.  Every ``forward`` returns a NEW handle with the next generation number; a handle
+    is single-use - passing an older one again (retry after an exception, branching, replaying) raises ``ValueError``
+    instead of silently advancing the stream twice.  The slots go back to the pool when the last handle of the group is
+    garbage collected, or deterministically through ``release()`` / use as a context manager."""
+
+    def __init__(self, engine: Engine, slots: np.ndarray, _core: Optional[_SlotCore] = None):
+        self._core = _core or _SlotCore(engine, slots)
+        self.gen = self._core.gen
+
+    @property
+    def engine(self) -> Engine:
+        return self._core.engine
+
+    @property
+    def slots(self) -> np.ndarray:
+        return self._core.slots
+
+    def _advance(self) -> "StreamSlots":
+        c = self._core
+        if c.closed:
+            raise ValueError("this state handle was released")
+        if self.gen != c.gen:
+            raise ValueError(f"stale state handle (generation {self.gen}, the streams are at {c.gen}): "
+                             "device-resident state is advanced in place and a handle is single-use")
+        c.gen += 1
+        return StreamSlots(c.engine, c.slots, c)
+
+    def release(self):
+        self._core.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+
     def __len__(self):
-        return len(self.slots)
+        return len(self._core.slots)
 
 
 class B200StreamingCTCModel:
@@ -313,7 +480,8 @@ class B200StreamingCTCModel:
 
     state_mode="numpy": ``forward`` takes/returns the reference's flat fp16 state ``(B, 219729)`` - each call
     imports the state into scratch slots, steps, and exports it again (parity / migration path; state crosses PCIe).
-    state_mode="device": state is a :class:`StreamSlots` handle; per-stream state stays in HBM (throughput path).
+    state_mode="device": state is a :class:`StreamSlots` handle; per-stream state stays in HBM (throughput path) and
+    is advanced in place - see :class:`StreamSlots` for the single-use handle contract.
     """
 
     SAMPLE_RATE = 8000            # reference: tone/onnx_wrapper.py:30-34
@@ -369,9 +537,7 @@ class B200StreamingCTCModel:
                 f"Shape of 'audio_chunk' must be (B, {self.AUDIO_CHUNK_SAMPLES}, 1), but got {audio_chunk.shape}")
         if audio_chunk.dtype != np.int32:
             raise ValueError(f"Incorrect dtype of 'audio_chunk': expected np.int32, but got {audio_chunk.dtype}")
-        if audio_chunk.min() < -32768 or audio_chunk.max() > 32767:
-            raise ValueError("Samples in 'audio_chunk' must be in range [-32768; 32767], "
-                             f"but it is in range [{audio_chunk.min()}; {audio_chunk.max()}]")
+        # the sample range [-32768; 32767] is checked by the C ABI while it narrows the PCM (TONE_ERANGE -> ValueError)
         B = audio_chunk.shape[0]
         pcm = audio_chunk[:, :, 0]
         eng = self.engine
@@ -382,8 +548,9 @@ class B200StreamingCTCModel:
                 raise TypeError(f"Incorrect 'state' type: expected StreamSlots or None, but got {type(state)}")
             if len(state) != B:
                 raise ValueError(f"'state' holds {len(state)} streams, but the batch has {B}")
+            nxt = state._advance()
             logprobs, _ = eng.step(state.slots, pcm, want_tokens=False)
-            return [logprobs, state]
+            return [logprobs, nxt]
         # numpy mode
         if state is None:
             state = np.zeros((B, self.STATE_SIZE), dtype=np.float16)
@@ -398,8 +565,6 @@ class B200StreamingCTCModel:
                 eng.release_slots(self._scratch)
             self._scratch = eng.alloc_slots(B)
         slots = self._scratch[:B]
-        for b in range(B):
-            eng.import_state(int(slots[b]), state[b])
+        eng.import_states(slots, state)
         logprobs, _ = eng.step(slots, pcm, want_tokens=False)
-        state_next = np.stack([eng.export_state(int(slots[b])) for b in range(B)], 0)
-        return [logprobs, state_next]
+        return [logprobs, eng.export_states(slots)]

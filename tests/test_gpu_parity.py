@@ -2,11 +2,15 @@
 on the same seeded inputs and against the committed reference golden vectors.
 
 Stated tolerance (floating point path, bf16 tensor-core operands with fp32 accumulation, fp32 norms / softmax):
-  logprobs  |d| <= 0.10 vs the fp32 oracle / reference goldens (observed bf16 operand-rounding spread is 0.05,
-            tests/test_oracle.py::test_bf16_emulation_within_stated_tolerance), <= 0.06 vs the bf16-emulating oracle
-  state     |d| <= 0.10 (fp16 wire format, values up to ~4.5), mhsa_len exact
-  tokens    identical wherever the oracle's top-2 logprob margin exceeds 0.10
+  logprobs  |d| <= 0.06 vs the fp32 oracle / reference goldens (measured on B200: 0.03 typical, 0.053 worst over a
+            one-hour stream; the bf16 operand-rounding spread of the reference algorithm itself is 0.05,
+            tests/test_oracle.py::test_bf16_emulation_within_stated_tolerance), <= 0.05 vs the bf16-emulating oracle
+  state     |d| <= 0.06 (fp16 wire format, values up to ~4.5; measured 0.02), mhsa_len exact
+  tokens    identical wherever the oracle's top-2 logprob margin exceeds the logprob tolerance
+  stages    residual stream after pre-encode and after every Conformer layer: per-stage bounds in STAGE_TOL
 """
+import json
+import os
 import numpy as np
 import pytest
 import torch
@@ -15,7 +19,7 @@ import tone_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-LP_TOL, LP_TOL_EMU, ST_TOL = 0.10, 0.06, 0.10
+LP_TOL, LP_TOL_EMU, ST_TOL = 0.06, 0.05, 0.06
 
 
 def _stream_oracle(W, pcm, C, quant=None):
@@ -47,10 +51,9 @@ def _check_tokens(tokens, lp_ref):
 def _check_state(eng, slots, st_ref):
     flat_ref = orc.pack_state(st_ref).astype(np.float32)
     len_off = 80 + 2 * 30 * 384 + 16 * 384 * 30
-    for b, s in enumerate(slots):
-        got = eng.export_state(int(s)).astype(np.float32)
-        assert got[len_off] == flat_ref[b, len_off]
-        assert np.abs(got - flat_ref[b]).max() <= ST_TOL
+    got = eng.export_states(slots).astype(np.float32)
+    assert np.array_equal(got[:, len_off], flat_ref[:, len_off])
+    assert np.abs(got - flat_ref).max() <= ST_TOL
 
 
 @pytest.fixture(scope="module")
@@ -98,7 +101,7 @@ def test_step_matches_reference_golden(engines, golden, ms, C):
         assert np.isfinite(lp).all()
         assert np.abs(lp - g["logprobs"]).max() <= LP_TOL
         _check_tokens(tk, g["logprobs"])
-        got = eng.export_state(int(slots[0])).astype(np.float32)
+        got = eng.export_state(int(slots[0])).astype(np.float32)          # the golden holds the state of stream 0
         ref = np.concatenate([g["state_" + k].astype(np.float32).reshape(-1) for k in orc.STATE_KEYS])
         assert np.abs(got - ref).max() <= ST_TOL
     finally:
@@ -129,17 +132,15 @@ def test_step_matches_oracle(engines, weights, tb, C, B, n):
 # ---- large-batch paths: 128-wide tiles (>= 2048 rows per lane), two concurrent lanes (>= 512 streams), and the
 # persistent GEMM kernel.  Streams are independent, so B streams that replay a handful of distinct signals must all
 # reproduce the oracle's answer for their signal (size-independent property; the oracle runs the distinct signals only).
-@pytest.mark.parametrize("C,B,persist,mode", [(2400, 600, None, None), (2400, 600, "0", "0"), (2400, 600, "1", "0"), (2400, 600, "1", "1"),
-                                               (2400, 600, "1", "2"), (3200, 420, "1", "2"), (2400, 230, "1", "2"),
-                                               (2400, 333, "1", "1")])
-def test_large_batch_paths_match_oracle(weights, tb, monkeypatch, C, B, persist, mode):
-    # persist: smallest GEMM (in 128 x 128 tiles) that takes the persistent kernel, 0 = never; mode: its tile form
-    # (0 = 128 wide, 1 = 256 wide, 2 = 256 wide on CTA pairs)
-    if persist is not None:   # None = the engine's defaults
-        monkeypatch.setenv("TONE_PERSIST_MIN_TILES", persist)
-        monkeypatch.setenv("TONE_PERSIST_MODE", mode)
+@pytest.mark.parametrize("C,B,persist,mode", [(2400, 600, 0, 0), (2400, 600, -1, 1), (2400, 600, 1, 1), (2400, 600, 1, 2),
+                                               (2400, 600, 1, 3), (3200, 420, 1, 3), (2400, 230, 1, 3),
+                                               (2400, 333, 1, 2)])
+def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode):
+    # persist: smallest GEMM (in 128 x 128 tiles) that takes the persistent kernel (tone_config.persist_min_tiles:
+    # 0 = default, -1 = never); mode: its tile form (tone_config.persist_mode: 0 = default, 1 = 128 wide, 2 = 256 wide,
+    # 3 = 256 wide on CTA pairs)
     n, D = 3, 6
-    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, persist_min_tiles=persist, persist_mode=mode)
     try:
         W = orc.to_torch(weights)
         distinct = tb.synth.telephony_pcm(D, C * n, seed=77)
@@ -153,54 +154,199 @@ def test_large_batch_paths_match_oracle(weights, tb, monkeypatch, C, B, persist,
         assert (tk == lp.argmax(-1)).all()
         _check_tokens(tk, ref[:, idx])
         flat_ref = orc.pack_state(st).astype(np.float32)
-        for b in (0, 1, B // 2, B - 2, B - 1):
-            got = eng.export_state(int(slots[b])).astype(np.float32)
-            assert np.abs(got - flat_ref[idx[b]]).max() <= ST_TOL
+        probe = np.array([0, 1, B // 2, B - 2, B - 1])
+        got = eng.export_states(slots[probe]).astype(np.float32)
+        assert np.abs(got - flat_ref[idx[probe]]).max() <= ST_TOL
     finally:
         eng.close()
 
 
-# ---- experimental cluster (latency) path: the 16 layers + decoder as one thread-block-cluster kernel
-@pytest.mark.parametrize("C,B,n,G", [(2400, 5, 5, None), (3200, 7, 4, None), (2400, 64, 3, None), (2400, 66, 2, "4"),
-                                     (2400, 78, 2, "5"), (3200, 50, 2, "3")])
-def test_cluster_path_matches_oracle(weights, tb, monkeypatch, C, B, n, G):
-    """Same parity bar as the per-kernel path.  Cases cover: a ragged last group (B not a multiple of the group size),
-    both group-size instantiations, and more groups than co-resident clusters (66 streams / 4 = 17 groups, 78 / 5 = 16,
-    50 / 3 = 17 against 15 clusters), where clusters loop over groups."""
-    if G is not None:
-        monkeypatch.setenv("TONE_CLUSTER_G", G)
-    eng = tb.Engine(weights, chunk_samples=C, max_slots=80, max_batch=80, cluster_max_batch=80)
+# ---- BASELINE configs[2] / configs[3] shapes: 1024 streams on one GPU (two lanes of 5120 rows: persistent gated GEMMs,
+# 128-wide tiles everywhere) and 4096 streams (the per-GPU share of 8192 streams on 2 GPUs; 20480 rows per lane).
+# 32 / 40 distinct signals replayed across the batch; every stream must reproduce the oracle's answer for its signal,
+# and the carried state of every stream is checked, not a sample.
+@pytest.mark.parametrize("C,B,D,n", [(2400, 1024, 32, 3), (3200, 1024, 32, 2), (2400, 4096, 40, 2)])
+def test_baseline_throughput_shapes_match_oracle(weights, tb, C, B, D, n):
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B)
     try:
         W = orc.to_torch(weights)
-        pcm = tb.synth.telephony_pcm(B, C * n, seed=300 + B)
+        distinct = tb.synth.telephony_pcm(D, C * n, seed=500 + B)
+        idx = (np.arange(B) * 7) % D                        # neighbours in the batch carry different signals
+        pcm = np.ascontiguousarray(distinct[idx])
         slots = eng.alloc_slots(B)
         lp, tk = _stream_engine(eng, slots, pcm, C)
-        assert eng._get_info().launches_per_step < 20       # the cluster kernel really ran
-        ref, st = _stream_oracle(W, pcm, C)
+        ref, st = _stream_oracle(W, distinct, C)
         assert np.isfinite(lp).all()
-        assert np.abs(lp - ref).max() <= LP_TOL
-        _check_tokens(tk, ref)
+        assert np.abs(lp - ref[:, idx]).max() <= LP_TOL
         assert (tk == lp.argmax(-1)).all()
-        _check_state(eng, slots, st)
+        _check_tokens(tk, ref[:, idx])
+        flat_ref = orc.pack_state(st).astype(np.float32)
+        len_off = 80 + 2 * 30 * 384 + 16 * 384 * 30
+        worst = 0.0
+        for i0 in range(0, B, 256):
+            got = eng.export_states(slots[i0:i0 + 256]).astype(np.float32)
+            want = flat_ref[idx[i0:i0 + 256]]
+            assert np.array_equal(got[:, len_off], want[:, len_off])
+            worst = max(worst, float(np.abs(got - want).max()))
+        assert worst <= ST_TOL
+        # streams that carry the same signal agree bit-exactly when they sit in the same lane (same kernel selection)
+        same = np.nonzero(idx[: B // 2] == idx[0])[0]
+        assert all(np.array_equal(lp[:, same[0]], lp[:, j]) for j in same[1:])
     finally:
         eng.close()
 
 
-def test_cluster_path_agrees_with_kernel_path_over_many_chunks(weights, tb):
-    """Both device paths carry the same state layout: run 12 chunks on each (first three exercise the key masks) and
-    compare logprobs and the exported state directly."""
-    C, B, n = 2400, 9, 12
-    pcm = tb.synth.telephony_pcm(B, C * n, seed=77)
-    outs = []
-    for cmb in (0, 80):
-        eng = tb.Engine(weights, chunk_samples=C, max_slots=16, max_batch=16, cluster_max_batch=cmb)
+# ---- per-stage parity: the residual stream after pre-encode and after every Conformer layer (tone_step_debug taps)
+# against the oracle's taps.  Bounds per stage are 2x what was measured on B200 (gpurun_out/stage_errors.json of the
+# same test, copied to profiles/r02_stage_errors.json): a regression of one stage cannot hide below the end-to-end
+# tolerance any more.
+STAGE_NAMES = ["pre_encode"] + [f"layer{l}" for l in range(16)]
+STAGE_TOL = {"fp32": dict.fromkeys(STAGE_NAMES, 0.25), "bf16emu": dict.fromkeys(STAGE_NAMES, 0.25)}
+
+
+@pytest.mark.parametrize("C", [2400, 3200])
+def test_per_stage_residual_stream_matches_oracle(weights, tb, C):
+    B, n = 5, 4
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=8, max_batch=8, use_graph=False)
+    try:
+        W = orc.to_torch(weights)
+        pcm = tb.synth.telephony_pcm(B, C * n, seed=1234)
         slots = eng.alloc_slots(B)
-        lp, _ = _stream_engine(eng, slots, pcm, C)
-        st = np.stack([eng.export_state(int(s)).astype(np.float32) for s in slots])
-        outs.append((lp, st))
+        st32, stemu = orc.zero_state(B), orc.zero_state(B)
+        worst = {"fp32": dict.fromkeys(STAGE_NAMES, 0.0), "bf16emu": dict.fromkeys(STAGE_NAMES, 0.0)}
+        scale = dict.fromkeys(STAGE_NAMES, 0.0)
+        for i in range(n):
+            chunk = pcm[:, i * C:(i + 1) * C]
+            t32, temu = {}, {}
+            _, st32 = orc.step(W, torch.from_numpy(chunk), st32, taps=t32)
+            _, stemu = orc.step(W, torch.from_numpy(chunk), stemu, quant=orc.bf16_round, taps=temu)
+            _, _, taps = eng.step_debug(slots, chunk)
+            for k, name in enumerate(STAGE_NAMES):
+                for mode, ref in (("fp32", t32), ("bf16emu", temu)):
+                    r = ref[name].numpy().reshape(-1, 384)
+                    d = float(np.abs(taps[k][: r.shape[0]] - r).max())
+                    worst[mode][name] = max(worst[mode][name], d)
+                scale[name] = max(scale[name], float(np.abs(t32[name].numpy()).max()))
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, f"stage_errors_{C}.json"), "w") as f:
+                json.dump({"chunk_samples": C, "streams": B, "chunks": n, "max_abs_err": worst, "ref_abs_max": scale}, f, indent=1)
+        for mode in worst:
+            for name in STAGE_NAMES:
+                assert worst[mode][name] <= STAGE_TOL[mode][name], (mode, name, worst[mode][name])
+    finally:
         eng.close()
-    assert np.abs(outs[0][0] - outs[1][0]).max() <= LP_TOL_EMU
-    assert np.abs(outs[0][1] - outs[1][1]).max() <= ST_TOL
+
+
+def test_bad_batches_are_rejected_by_the_c_abi(engines, tb):
+    """Duplicate / unallocated / out-of-range slot ids and out-of-range samples are errors, not silent corruption
+    (tone/onnx_wrapper.py:100-121 for the sample range)."""
+    eng = engines(2400)
+    slots = eng.alloc_slots(3)
+    try:
+        pcm = tb.synth.telephony_pcm(3, 2400, seed=1)
+        with pytest.raises(ValueError, match="twice"):
+            eng.step(np.array([slots[0], slots[1], slots[0]], dtype=np.int32), pcm)
+        with pytest.raises(ValueError, match="out of range"):
+            eng.step(np.array([slots[0], 10 ** 6, slots[1]], dtype=np.int32), pcm)
+        free = [s for s in range(80) if s not in set(slots.tolist())][0]
+        with pytest.raises(tb.model.ToneError, match="not allocated"):
+            eng.step(np.array([slots[0], free, slots[1]], dtype=np.int32), pcm)
+        with pytest.raises(ValueError, match="twice"):
+            eng.step_device(np.array([slots[2], slots[2]], dtype=np.int32), 0)
+        bad = pcm.copy()
+        bad[1, 100] = 40000
+        before = eng.export_states(slots)
+        with pytest.raises(ValueError, match=r"range \[-32768; 32767\]"):
+            eng.step(slots, bad)
+        assert np.array_equal(before, eng.export_states(slots))      # a rejected step leaves the state untouched
+        eng.step(slots, pcm)                                          # and the engine keeps working
+    finally:
+        eng.release_slots(slots)
+
+
+def test_int16_wire_format_and_pipelined_tickets_are_bit_identical(engines, tb):
+    """tone_submit / tone_wait with int16 PCM and two tickets in flight == the synchronous int32 call."""
+    C, B, n = 2400, 9, 6
+    eng = engines(C)
+    pcm = tb.synth.telephony_pcm(B, C * n, seed=61)
+    s1, s2 = eng.alloc_slots(B), eng.alloc_slots(B)
+    try:
+        want, _ = _stream_engine(eng, s1, pcm, C)
+        got, pending = [], None
+        for i in range(n):
+            stg_slots, stg_pcm, _ = eng.next_staging(B)             # zero-copy staging of the next set
+            stg_slots[:] = s2
+            stg_pcm[:] = pcm[:, i * C:(i + 1) * C].astype(np.int16)
+            t = eng.submit(stg_slots, stg_pcm, tb.model.OUT_LOGPROBS | tb.model.OUT_TOKENS | tb.model.OUT_SIL)
+            if pending is not None:
+                got.append(eng.wait(pending))
+            pending = t
+        got.append(eng.wait(pending))
+        for i in range(n):
+            assert np.array_equal(got[i]["logprobs"], want[i])
+            assert np.array_equal(got[i]["tokens"], want[i].argmax(-1))
+            assert np.array_equal(got[i]["sil"], want[i][:, :, 33:35])
+        with pytest.raises(tb.model.ToneError, match="not in flight"):
+            eng.wait(pending)
+        t1 = eng.submit(s1, pcm[:, :C])
+        t2 = eng.submit(s2, pcm[:, :C])
+        with pytest.raises(tb.model.ToneError, match="not been waited"):
+            eng.submit(s1, pcm[:, :C])                                # both staging sets are busy
+        eng.wait(t1)
+        eng.wait(t2)
+    finally:
+        eng.release_slots(np.concatenate([s1, s2]))
+
+
+def test_caller_stream_is_ordered_with_engine_streams(engines, tb):
+    """a step launched on the caller's stream must see the staged inputs, and fetch must see its outputs,
+    without the caller synchronising anything."""
+    C, B = 2400, 8
+    eng = engines(C)
+    pcm = tb.synth.telephony_pcm(B, C * 4, seed=88)
+    s1, s2 = eng.alloc_slots(B), eng.alloc_slots(B)
+    side = torch.cuda.Stream()
+    try:
+        want, _ = _stream_engine(eng, s1, pcm, C)
+        for i in range(4):
+            eng.stage(s2, pcm[:, i * C:(i + 1) * C])
+            eng.step_staged(B, side.cuda_stream)
+            lp, tk = eng.fetch(B)
+            assert np.array_equal(lp, want[i])
+        # device-pointer form on the caller's stream, int16 and int32 device PCM
+        eng.reset_slots(s2)
+        for i in range(4):
+            x = torch.from_numpy(pcm[:, i * C:(i + 1) * C].astype(np.int16 if i % 2 else np.int32)).cuda()
+            d_lp = torch.empty((B, eng.T, 35), dtype=torch.float32, device="cuda")
+            with torch.cuda.stream(side):
+                eng.step_device(s2, x.data_ptr(), tb.model.PCM_I16 if i % 2 else tb.model.PCM_I32, d_lp.data_ptr(), 0,
+                                side.cuda_stream)
+            side.synchronize()
+            assert np.array_equal(d_lp.cpu().numpy(), want[i])
+    finally:
+        eng.release_slots(np.concatenate([s1, s2]))
+
+
+def test_triton_three_tensor_state_through_the_c_abi(engines, tb):
+    """tone_export/import_states_triton == the Python restatement of tone/scripts/export.py:293-376 on the flat state."""
+    C, B = 2400, 3
+    eng = engines(C)
+    pcm = tb.synth.telephony_pcm(B, C * 3, seed=91)
+    s1, s2 = eng.alloc_slots(B), eng.alloc_slots(B)
+    try:
+        _stream_engine(eng, s1, pcm[:, :2 * C], C)
+        flat = eng.export_states(s1)
+        tm, ch, ln = eng.export_states_triton(s1)
+        tm2, ch2, ln2 = tb.state_formats.flat_to_triton(flat)
+        assert np.array_equal(tm, tm2) and np.array_equal(ch, ch2) and np.array_equal(ln, ln2)
+        eng.import_states_triton(s2, tm, ch, ln)
+        assert np.array_equal(eng.export_states(s2), flat)
+        la, _ = eng.step(s1, pcm[:, 2 * C:])
+        lb, _ = eng.step(s2, pcm[:, 2 * C:])
+        assert np.abs(la - lb).max() < 3e-2
+    finally:
+        eng.release_slots(np.concatenate([s1, s2]))
 
 
 def test_feature_input_mode(engines, weights, tb):

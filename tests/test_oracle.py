@@ -9,7 +9,7 @@ import torch
 
 import tone_oracle as orc
 
-REF = os.environ.get("TONE_REFERENCE", "/root/reference")
+import refimport
 
 
 def _run(W, pcm, C, quant=None):
@@ -87,15 +87,15 @@ def test_stream_independence(weights, tb):
 
 
 def test_bf16_emulation_within_stated_tolerance(weights, tb):
-    """The tolerance the GPU parity tests state (logprobs 0.1, state 0.1) covers operand rounding to bf16."""
+    """The tolerance the GPU parity tests state (logprobs 0.06, state 0.06) covers operand rounding to bf16."""
     W = orc.to_torch(weights)
     pcm = tb.synth.telephony_pcm(2, 2400 * 4, seed=11)
     a, sa = _run(W, pcm, 2400)
     b, sb = _run(W, pcm, 2400, quant=orc.bf16_round)
-    assert np.abs(a - b).max() < 0.1
+    assert np.abs(a - b).max() < 0.06
     for k in orc.STATE_KEYS:
         if k != "mhsa_len":
-            assert float((sa[k] - sb[k]).abs().max()) < 0.1
+            assert float((sa[k] - sb[k]).abs().max()) < 0.06
 
 
 def test_greedy_text():
@@ -113,13 +113,15 @@ def test_frontend_constants_match_torchaudio(tb):
     assert int((fb != 0).sum()) == 156
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tone", "nn")), reason="reference tree not mounted")
+@pytest.mark.skipif(refimport.reference_root() is None, reason="no reference tree reachable")
 def test_oracle_matches_live_reference(tb, weights):
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import make_golden as mg
+    """The unmodified reference torch model (from /root/reference or its installed copy baseline/_ref), run live."""
     pcm = tb.synth.telephony_pcm(2, 2400 * 3, seed=77)
-    chunks = [np.ascontiguousarray(pcm[:, i * 2400:(i + 1) * 2400]) for i in range(3)]
-    outs, _ = mg.reference_stream(weights, chunks, "fp32")
+    model = refimport.ReferenceStreamingModel(weights)
+    state, outs = None, []
+    for i in range(3):
+        lp_ref, state = model.forward(np.ascontiguousarray(pcm[:, i * 2400:(i + 1) * 2400, None]).astype(np.int32), state)
+        outs.append(lp_ref)
     lp, _ = _run(orc.to_torch(weights), pcm, 2400)
     np.testing.assert_allclose(lp, np.stack(outs, 0), atol=1e-4, rtol=0)
 

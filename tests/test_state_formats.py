@@ -7,7 +7,7 @@ import pytest
 
 import tone_oracle as orc
 
-REF = os.environ.get("TONE_REFERENCE", "/root/reference")
+REF = os.environ.get("TONE_REFERENCE", "/root/reference")   # Triton configs are not part of the installed package
 
 
 def _random_flat(B=2, seed=0):
@@ -67,7 +67,7 @@ def test_engine_state_through_triton_layout(tb, weights):
     a, b = eng.alloc_slots(2), eng.alloc_slots(2)
     for i in range(2):
         eng.step(a, pcm[:, i * 2400:(i + 1) * 2400])
-    flat = np.stack([eng.export_state(int(s)) for s in a])
+    flat = eng.export_states(a)
     t, c, n = tb.state_formats.flat_to_triton(flat)
     back = tb.state_formats.triton_to_flat(t, c, n)
     np.testing.assert_array_equal(back, flat)
