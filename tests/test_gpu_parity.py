@@ -201,7 +201,12 @@ def test_baseline_throughput_shapes_match_oracle(weights, tb, C, B, D, n):
 # same test, copied to profiles/r02_stage_errors.json): a regression of one stage cannot hide below the end-to-end
 # tolerance any more.
 STAGE_NAMES = ["pre_encode"] + [f"layer{l}" for l in range(16)]
-STAGE_TOL = {"fp32": dict.fromkeys(STAGE_NAMES, 0.25), "bf16emu": dict.fromkeys(STAGE_NAMES, 0.25)}
+# measured max |d| on B200 (profiles/r02_stage_errors_{2400,3200}.json), worst of the two chunk lengths
+_MEASURED = {"fp32": [0.0158, 0.0160, 0.0162, 0.0181, 0.0178, 0.0190, 0.0185, 0.0082, 0.0187, 0.0200, 0.0215, 0.0234, 0.0226,
+                      0.0304, 0.0349, 0.0309, 0.0287],
+             "bf16emu": [0.0017, 0.0033, 0.0042, 0.0053, 0.0057, 0.0069, 0.0091, 0.0039, 0.0112, 0.0121, 0.0134, 0.0155, 0.0141,
+                         0.0206, 0.0198, 0.0206, 0.0179]}
+STAGE_TOL = {mode: {name: 2.0 * v for name, v in zip(STAGE_NAMES, vals)} for mode, vals in _MEASURED.items()}
 
 
 @pytest.mark.parametrize("C", [2400, 3200])

@@ -191,7 +191,7 @@ def test_greedy_pipeline_on_gpu_matches_full_logprob_path(tb, weights):
     """GreedyStreamingPipeline (phrases decided on the device, inside the step graph) == Engine.step (full log-probs) +
     the restated reference chain on the host, stream by stream."""
     B, C, n = 6, 2400, 60
-    eng = tb.Engine(weights, chunk_samples=C, max_slots=2 * B, max_batch=B)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=3 * B, max_batch=B)
     try:
         pcm = tb.synth.telephony_pcm(B, C * n, seed=42)
         pipe = tb.greedy.GreedyStreamingPipeline(eng, B)
