@@ -30,6 +30,7 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "ctc_phrase.cuh"
+#include "ff_fused.cuh"
 #include "state_io.cuh"
 
 using namespace tone;
@@ -95,6 +96,7 @@ struct WeightMat {      // a bf16 [N][K] matrix on the device with its TMA map (
   int N = 0, K = 0;
   CUtensorMap map;
   CUtensorMap map128;   // same matrix, box 64 x 128: the large-batch tile shape (valid when N % 128 == 0)
+  CUtensorMap map64;    // box 64 x 64: one CTA's half of a weight tile in the CTA-pair kernels (valid when N % 64 == 0)
 };
 
 struct LayerW {
@@ -223,6 +225,9 @@ struct tone_engine {
   // it has the GPU to itself, but with two lanes in flight the 256-wide single-CTA form gives the faster step.
   int persist_mode = 1;
   int split_k = 0;         // 0 = fill the SMs once
+  // Feed-forward module as ONE kernel per row tile (ff_fused.cuh) from ff_fused_min_rows rows per lane on:
+  // 0 = off, 1 = one CTA per 128 rows, 2 = CTA pairs (cta_group::2, 256 rows per pair)
+  int ff_fused = 2, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
   int num_sms = 148;
 };
@@ -286,6 +291,10 @@ static int upload_mat(tone_engine* e, const std::vector<float>& w, int N, int K,
     int rc = make_map_2d(e, &out->map128, p, N, K, 128, true);
     if (rc) return rc;
   }
+  if (N % 64 == 0) {
+    int rc = make_map_2d(e, &out->map64, p, N, K, 64, true);
+    if (rc) return rc;
+  }
   return make_map_2d(e, &out->map, p, N, K, box_rows, true);
 }
 static const HostTensor* W(tone_engine* e, const std::string& name) {
@@ -330,7 +339,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   if (cfg->max_slots < 1 || cfg->max_batch < 1 || cfg->max_batch > cfg->max_slots)
     return fail(TONE_EINVAL, "need 1 <= max_batch <= max_slots");
   if (cfg->lanes < 0 || cfg->lanes > 4 || cfg->persist_mode < 0 || cfg->persist_mode > 3 || cfg->split_k < 0 ||
-      cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0)
+      cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0 || cfg->fused_ff < 0 || cfg->fused_ff > 3 || cfg->fused_ff_min_rows < 0)
     return fail(TONE_EINVAL, "tuning field out of range (lanes 0..4, persist_mode 0..3, split_k 0..%d)", (int)MAX_SPLITS);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -364,6 +373,8 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->fuse_vatt = !(cfg->flags & TONE_FLAG_NO_FUSED_VATT);
   e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
   e->split_k = cfg->split_k;
+  if (cfg->fused_ff) e->ff_fused = cfg->fused_ff - 1;
+  if (cfg->fused_ff_min_rows) e->ff_fused_min_rows = cfg->fused_ff_min_rows;
   if (cfg->lanes) e->n_lanes = cfg->lanes;
   if (cfg->lane_min_batch) e->lane_min_batch = cfg->lane_min_batch;
   e->C = cfg->chunk_samples;
@@ -523,6 +534,8 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_gemm_tc_persist<G_RESID, 1, false>()));
   CK((configure_gemm_tc_persist<G_STORE_F32, 1, false>()));
   CK((configure_gemm_tc_persist<G_PARTIAL, 1, false>()));
+  CK((configure_ff_fused<false>()));
+  CK((configure_ff_fused<true>()));
   e->persist_ctas = e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
@@ -1103,6 +1116,42 @@ static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M,
   return 0;
 }
 
+// The whole feed-forward module in one kernel per row tile (ff_fused.cuh): r += 0.5 FF(a); [r = norm(r; g1)];
+// n = norm(r; g2) (bf16, optionally scattered into the [cache | new] rows of a stateful attention layer).
+static bool use_ff_fused(const tone_engine* e, int M) {
+  return e->cfg.gemm_impl == 0 && e->ff_fused > 0 && M >= e->ff_fused_min_rows;
+}
+static int run_ff_fused(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, float* r, const WeightMat& up,
+                        const float* up_b, const WeightMat& down, const float* down_b, int ss_tiles, const float* g1,
+                        const float* g2, bf16* n_out, bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
+  FfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M;
+  a.up_bias = up_b;
+  a.down_bias = down_b;
+  if (ss_tiles) {
+    a.ss = ln.ss;
+    a.ss_ld = 12;
+    a.ss_tiles = ss_tiles;
+  }
+  a.r = r;
+  a.scale = 0.5f;
+  a.g1 = g1;
+  a.g2 = g2;
+  a.n = n_out;
+  a.kv = kv;
+  a.slots = ln.slots;
+  a.rows_per_stream = rows_per_stream;
+  a.kv_row_off = kv_row_off;
+  const CUtensorMap& mA = ss_tiles ? ln.m_rb : ln.m_n;
+  const int mt = (M + 127) / 128;
+  cudaError_t err = e->ff_fused == 2 ? launch_ff_fused<true>(st, mA, up.map64, down.map, down.map64, a, mt, e->pdl)
+                                     : launch_ff_fused<false>(st, mA, up.map, down.map, down.map, a, mt, e->pdl);
+  e->launches++;
+  if (err != cudaSuccess) return fail(TONE_ECUDA, "fused feed-forward launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
 // r += A W^T + b through the tensor cores; also emits bf16(r) and the per-tile row sums of squares that let the next
 // GEMM apply the following RMSNorm as a row scale.  Returns the number of ss tiles through *ss_tiles.
 static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const bf16* A,
@@ -1218,7 +1267,15 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     M = B * Tl;
     const int mt = (M + 127) / 128;
     PartIn ff;
-    RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
+    const bool fused_ff = use_ff_fused(e, M);
+    if (fused_ff) {   // feed-forward 1 + residual + norm_self_att (+ cache-row scatter of layers 14 / 15) in one kernel
+      if (l < 14) RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n));
+      else
+        RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n,
+                        l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
+    } else {
+      RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
+    }
     // ---- attention (its norm kernel first folds the feed-forward output into r)
     AttnArgs at;
     memset(&at, 0, sizeof(at));
@@ -1231,7 +1288,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     at.recompute = RECOMPUTE[l] ? 1 : 0;
     bool fused_att = false;
     if (l < 14) {
-      RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
@@ -1275,7 +1332,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     } else {
       const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
       bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
-      RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
       float* qbuf = ln.qkv;
       float* kvout = ln.qkv + (size_t)e->rows_alloc * D_MODEL;
       GemmArgs a = dense_args(M, D_MODEL, ln.n, qbuf, D_MODEL, L.q_b, 1.f);
@@ -1340,9 +1397,17 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     }
     RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles));
     // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer
-    RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff, ss_tiles));
+    if (fused_ff) {   // feed-forward 2 + residual + norm_out + the next layer's first norm in one kernel
+      const float* g1 = l == 14 ? nullptr : L.n_out;
+      const float* g2 = (l == 6 || l >= 14) ? nullptr : e->L[l + 1].n_ff1;
+      bf16* n_out = (l == 6 || l == 14) ? nullptr : ln.n;
+      RC(run_ff_fused(e, ln, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, ss_tiles, g1, g2, n_out));
+      ff = PartIn();
+    } else {
+      RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff, ss_tiles));
+    }
     if (l == 6) {
-      RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{ln.r_full, e->st_red, ln.slots, e->red_dw_w, e->red_dw_b, ln.m_red, T, T2};
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
@@ -1358,10 +1423,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       else KLAUNCH(launch_kernel(upsample_norm_kernel<2>, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, ln.r_full, B * T));
     } else if (l == 15) {
-      RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     } else {
-      RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     }
   }

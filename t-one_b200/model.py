@@ -41,7 +41,8 @@ class ToneConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_samples", C.c_int32), ("max_slots", C.c_int32),
                 ("max_batch", C.c_int32), ("gemm_impl", C.c_int32), ("use_graph", C.c_int32),
                 ("lanes", C.c_int32), ("lane_min_batch", C.c_int32), ("persist_min_tiles", C.c_int32),
-                ("persist_mode", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32)]
+                ("persist_mode", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32),
+                ("fused_ff", C.c_int32), ("fused_ff_min_rows", C.c_int32)]
 
 
 class ToneInfo(C.Structure):
@@ -156,11 +157,12 @@ class Engine:
 
     def __init__(self, weights=None, chunk_samples: int = 2400, max_slots: int = 64, max_batch: Optional[int] = None,
                  device: int = 0, gemm_impl: int = 0, use_graph: bool = True, *, lanes: int = 0, lane_min_batch: int = 0,
-                 persist_min_tiles: int = 0, persist_mode: int = 0, split_k: int = 0, flags: int = 0):
+                 persist_min_tiles: int = 0, persist_mode: int = 0, split_k: int = 0, flags: int = 0,
+                 fused_ff: int = 0, fused_ff_min_rows: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph),
-                         lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags)
+                         lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags, fused_ff, fused_ff_min_rows)
         rc = self._lib.tone_create(C.byref(cfg), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

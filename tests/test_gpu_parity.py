@@ -132,15 +132,20 @@ def test_step_matches_oracle(engines, weights, tb, C, B, n):
 # ---- large-batch paths: 128-wide tiles (>= 2048 rows per lane), two concurrent lanes (>= 512 streams), and the
 # persistent GEMM kernel.  Streams are independent, so B streams that replay a handful of distinct signals must all
 # reproduce the oracle's answer for their signal (size-independent property; the oracle runs the distinct signals only).
-@pytest.mark.parametrize("C,B,persist,mode", [(2400, 600, 0, 0), (2400, 600, -1, 1), (2400, 600, 1, 1), (2400, 600, 1, 2),
-                                               (2400, 600, 1, 3), (3200, 420, 1, 3), (2400, 230, 1, 3),
-                                               (2400, 333, 1, 2)])
-def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode):
+@pytest.mark.parametrize("C,B,persist,mode,ff", [(2400, 600, 0, 0, (0, 0)), (2400, 600, -1, 1, (1, 0)), (2400, 600, 1, 1, (1, 0)),
+                                                  (2400, 600, 1, 2, (1, 0)), (2400, 600, 1, 3, (1, 0)), (3200, 420, 1, 3, (1, 0)),
+                                                  (2400, 230, 1, 3, (1, 0)), (2400, 333, 1, 2, (1, 0)),
+                                                  (2400, 230, 0, 0, (2, 1)), (2400, 230, 0, 0, (3, 1)), (3200, 333, 0, 0, (3, 1)),
+                                                  (2400, 600, 0, 0, (2, 0)), (2400, 37, 0, 0, (3, 1))])
+def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode, ff):
     # persist: smallest GEMM (in 128 x 128 tiles) that takes the persistent kernel (tone_config.persist_min_tiles:
     # 0 = default, -1 = never); mode: its tile form (tone_config.persist_mode: 0 = default, 1 = 128 wide, 2 = 256 wide,
-    # 3 = 256 wide on CTA pairs)
+    # 3 = 256 wide on CTA pairs); ff = (tone_config.fused_ff, fused_ff_min_rows): fused feed-forward kernel
+    # 1 = off, 2 = one CTA per 128 rows, 3 = CTA pairs (default from 2048 rows per lane; min_rows 1 forces it for every
+    # layer, which also covers odd tile counts and ragged last tiles)
     n, D = 3, 6
-    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, persist_min_tiles=persist, persist_mode=mode)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, persist_min_tiles=persist, persist_mode=mode,
+                    fused_ff=ff[0], fused_ff_min_rows=ff[1])
     try:
         W = orc.to_torch(weights)
         distinct = tb.synth.telephony_pcm(D, C * n, seed=77)
