@@ -80,8 +80,8 @@ typedef struct tone_config {
                              /* 3 = 256-wide on CTA pairs (cta_group::2)                                     */
   int32_t split_k;           /* split-K factor of the feed-forward down projection (default: fill the SMs)   */
   int32_t flags;             /* TONE_FLAG_* bits                                                             */
-  int32_t fused_ff;          /* feed-forward module as one kernel per row tile: 1 = off, 2 = one CTA per 128 rows,   */
-                             /* 3 = CTA pairs (default)                                                      */
+  int32_t fused_ff;          /* feed-forward module as one kernel per row tile (experimental, opt-in):       */
+                             /* 1 = off (default), 2 = one CTA per 128 rows, 3 = CTA pairs                   */
   int32_t fused_ff_min_rows; /* rows per lane from which the fused feed-forward is used (default 2048)       */
 } tone_config;
 

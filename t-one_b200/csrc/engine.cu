@@ -226,8 +226,9 @@ struct tone_engine {
   int persist_mode = 1;
   int split_k = 0;         // 0 = fill the SMs once
   // Feed-forward module as ONE kernel per row tile (ff_fused.cuh) from ff_fused_min_rows rows per lane on:
-  // 0 = off, 1 = one CTA per 128 rows, 2 = CTA pairs (cta_group::2, 256 rows per pair)
-  int ff_fused = 2, ff_fused_min_rows = 2048;
+  // 0 = off (default), 1 = one CTA per 128 rows, 2 = CTA pairs (cta_group::2, 256 rows per pair).  Opt-in: parity-green,
+  // but at 1024 streams per GPU 80 row tiles cannot fill 148 SMs (profiles/r02_fused_ff.md).
+  int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
   int num_sms = 148;
 };

@@ -54,9 +54,11 @@ struct FfCfg {
   static constexpr int DN_SLAB = PAIR ? 192 * 128 : 384 * 128;      // this CTA's share of W2[:, chunk]
   static constexpr int S_DN = PAIR ? 2 : 1;
   static constexpr int VEC_BYTES = 3 * 384 * 4;                     // b2 | g1 | g2
-  static constexpr int SSQ_BYTES = 2 * 2 * 128 * 4;                 // [sum x^2 | sum (g1 x)^2][column half][row]
-  static constexpr int SMEM_BYTES = A_BYTES + H_BYTES + S_UP * UP_STG + S_DN * DN_SLAB + VEC_BYTES + SSQ_BYTES + 256 + 1024;
+  static constexpr int OPER_BYTES = A_BYTES + H_BYTES + S_UP * UP_STG + S_DN * DN_SLAB;
+  static constexpr int X_PITCH = 388;                               // floats per staged row of the final epilogue (conflict-free)
+  static constexpr int SMEM_BYTES = OPER_BYTES + VEC_BYTES + 256 + 1024;
   static_assert(SMEM_BYTES <= 232448, "does not fit");
+  static_assert(128 * X_PITCH * 4 <= OPER_BYTES, "the x tile is staged over the dead operand buffers");
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -68,12 +70,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// arrive on a barrier of the leader CTA (PAIR) or of this CTA
-template <bool PAIR>
-__device__ __forceinline__ void ff_arrive(uint64_t* bar) {
-  if constexpr (PAIR) mbar_arrive_cluster(map_to_rank(smem_u32(bar), 0));
-  else mbar_arrive(bar);
+// Signals from the epilogue warps to the MMA warp of the leader CTA.  `mbarrier.arrive.release.cluster` costs ~1500 cycles
+// per use (measured: it was 40 % of the per-chunk epilogue), so it is kept off the epilogue warps:
+//  * "accumulator drained" carries no data written by these threads (the tcgen05 fence orders the TMEM reads): leader
+//    warps arrive at CTA scope, peer warps with a relaxed cluster-scope arrive;
+//  * "hidden chunk written" is a CTA-scope arrive on the CTA's OWN barrier; in the peer CTA the otherwise idle warp 1
+//    relays each completed phase to the leader with one release.cluster arrive.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// remote arrive with the default semantics (release at CTA scope): what CUTLASS' ClusterBarrier::arrive(cta_id) emits
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// silu(x) * y with silu(x) = x * (0.5 + 0.5 tanh(x / 2)): one MUFU op per element (tanh.approx, |err| < 1e-3 relative,
+// far below the bf16 rounding of the result)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_mul(float x, float y) { return x * fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f) * y; }
 
 template <bool PAIR>
 __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -88,8 +105,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
   uint8_t* sUp = sH + Cfg::H_BYTES;
   uint8_t* sDn = sUp + Cfg::S_UP * Cfg::UP_STG;
   float* s_vec = reinterpret_cast<float*>(sDn + Cfg::S_DN * Cfg::DN_SLAB);        // b2[384] | g1[384] | g2[384]
-  float* s_ssq = s_vec + 3 * 384;                                                  // [2][2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ssq + 2 * 2 * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 3 * 384);
   uint64_t* up_full = bars;                      // [S_UP]
   uint64_t* up_empty = up_full + Cfg::S_UP;      // [S_UP]
   uint64_t* dn_full = up_empty + Cfg::S_UP;      // [S_DN]
@@ -127,7 +143,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
     mbar_init(a_full, 1);
     mbar_init(upacc_full, 1);
     mbar_init(upacc_empty, 8 * NCTA);            // one arrive per epilogue warp (of both CTAs)
-    mbar_init(h_full, 8 * NCTA);
+    mbar_init(h_full, 8 * NCTA);                 // every epilogue warp of the pair arrives on the leader's barrier
     mbar_init(h_empty, 1);
     mbar_init(dnacc_full, 1);
     fence_mbar_init();
@@ -209,10 +225,16 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
         else umma_commit(bar);
       };
       int up_cnt = 0;
+#ifdef TONE_PROF
+      long long w_up = 0, w_acc = 0, w_h = 0, w_dn = 0, t_;
+#define FF_TIMED(acc_, stmt) t_ = clock64(); stmt; acc_ += clock64() - t_
+#else
+#define FF_TIMED(acc_, stmt) stmt
+#endif
       auto down = [&](int i) {
         const int s = i % Cfg::S_DN;
-        mbar_wait(h_full, i & 1);
-        mbar_wait(&dn_full[s], (i / Cfg::S_DN) & 1);
+        FF_TIMED(w_h, mbar_wait(h_full, i & 1));
+        FF_TIMED(w_dn, mbar_wait(&dn_full[s], (i / Cfg::S_DN) & 1));
         tc_fence_after();
         const uint64_t dh = make_sw128_desc(sH_u);
         const uint64_t d0 = make_sw128_desc(sDn_u + s * Cfg::DN_SLAB);
@@ -229,12 +251,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
         __syncwarp();
       };
       mbar_wait(a_full, 0);
+#ifdef TONE_PROF
+      long long tm[5] = {0, 0, 0, 0, 0};
+      long long tch[FF_CHUNKS + 1];
+      const long long t_loop0 = clock64();
+#endif
       for (int j = 0; j < FF_CHUNKS; ++j) {
-        mbar_wait(upacc_empty, (j & 1) ^ 1);     // the epilogue has drained the previous chunk's accumulator
+#ifdef TONE_PROF
+        if (j == 12) tm[0] = clock64();
+        tch[j] = clock64();
+#endif
+        FF_TIMED(w_acc, mbar_wait(upacc_empty, (j & 1) ^ 1));     // the epilogue has drained the previous chunk's accumulator
         tc_fence_after();
         for (int k = 0; k < FF_KB; ++k, ++up_cnt) {
           const int s = up_cnt % Cfg::S_UP;
-          mbar_wait(&up_full[s], (up_cnt / Cfg::S_UP) & 1);
+          FF_TIMED(w_up, mbar_wait(&up_full[s], (up_cnt / Cfg::S_UP) & 1));
           tc_fence_after();
           const uint64_t da = make_sw128_desc(sA_u + k * 128 * 128);
           const uint64_t db = make_sw128_desc(sUp_u + s * Cfg::UP_STG);
@@ -245,13 +276,39 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
           }
           __syncwarp();
         }
+#ifdef TONE_PROF
+        if (j == 12) tm[1] = clock64();
+#endif
         if (elect_one_sync()) commit(upacc_full);
         __syncwarp();
+#ifdef TONE_PROF
+        if (j == 12) tm[2] = clock64();
+#endif
         if (j > 0) down(j - 1);
+#ifdef TONE_PROF
+        if (j == 12) tm[3] = clock64();
+        if (j == 13) tm[4] = clock64();
+#endif
       }
       down(FF_CHUNKS - 1);
       if (elect_one_sync()) commit(dnacc_full);
       __syncwarp();
+#ifdef TONE_PROF
+      if (lane == 0 && blockIdx.x == 0 && g_prof) {
+        tch[FF_CHUNKS] = clock64();
+        printf("ff loop: start %lld | chunk starts rel: %lld %lld %lld %lld %lld %lld %lld %lld %lld end %lld\n", t_loop0 - g_prof[prof_seq_s].c[0],
+               tch[0] - t_loop0, tch[1] - t_loop0, tch[2] - t_loop0, tch[3] - t_loop0, tch[6] - t_loop0, tch[12] - t_loop0,
+               tch[18] - t_loop0, tch[22] - t_loop0, tch[23] - t_loop0, tch[24] - t_loop0);
+      }
+      if (lane == 0 && blockIdx.x == 0 && g_prof)
+        printf("ff mma chunk12: wait_upacc_empty+U issue %lld commit %lld down(11) %lld  iter %lld | stalls up %lld acc %lld h %lld dn %lld\n",
+               tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[0] - (tm[4] - tm[3]) + (tm[4] - tm[3]), w_up, w_acc, w_h, w_dn);
+      if (lane == 0 && blockIdx.x == 0 && g_prof) {   // stall cycles of the MMA warp: up weights | up-acc drain | hidden chunk | down weights
+        g_prof[prof_seq_s].c[1] = g_prof[prof_seq_s].c[0] + w_up;
+        g_prof[prof_seq_s].c[2] = g_prof[prof_seq_s].c[0] + w_acc;
+        g_prof[prof_seq_s].c[3] = g_prof[prof_seq_s].c[0] + w_h + w_dn;
+      }
+#endif
     }
   } else {
     // ---------------- epilogue warps 2..9: warp w owns TMEM lanes 32 (w % 4) .. +31 and column half hf = (w - 2) / 4
@@ -276,11 +333,19 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
       rs = 1.0f / (sqrtf(t) * 0.05103103630798288f + 1e-8f);
     }
     const uint32_t h_row = smem_u32(sH) + row_in_tile * 128;
+#ifdef TONE_PROF
+    long long ts[6] = {0, 0, 0, 0, 0, 0};
+#define FF_TS(i) if (j == 12) ts[i] = clock64()
+#else
+#define FF_TS(i)
+#endif
     for (int j = 0; j < FF_CHUNKS; ++j) {
       // biases of this thread's 32 gate / 32 value columns (identical for every lane: broadcast loads)
       const float4* bg = reinterpret_cast<const float4*>(a.up_bias + j * 128 + hf * 32);
       const float4* bv = reinterpret_cast<const float4*>(a.up_bias + j * 128 + 64 + hf * 32);
+      FF_TS(0);
       mbar_wait(upacc_full, j & 1);
+      FF_TS(1);
       tc_fence_after();
       uint32_t g[32], v[32];
       tmem_ld16_async(upacc + lane_base + hf * 32, g);
@@ -294,7 +359,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
       tmem_regs_ready16(v + 16);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) ff_arrive<PAIR>(upacc_empty);            // the next chunk's up GEMM may overwrite the accumulator
+      if (lane == 0) {                                        // the next chunk's up GEMM may overwrite the accumulator
+        if (PAIR && !leader) mbar_arrive_cluster_relaxed(map_to_rank(smem_u32(upacc_empty), 0));
+        else mbar_arrive(upacc_empty);
+      }
+      FF_TS(2);
       uint32_t hp[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
@@ -303,11 +372,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
         float o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          o[i] = silu_f(fmaf(__uint_as_float(g[c + i]), rs, gb[i])) * fmaf(__uint_as_float(v[c + i]), rs, vb[i]);
+          o[i] = silu_mul(fmaf(__uint_as_float(g[c + i]), rs, gb[i]), fmaf(__uint_as_float(v[c + i]), rs, vb[i]));
         hp[(c >> 1)] = pack_bf16x2(o[0], o[1]);
         hp[(c >> 1) + 1] = pack_bf16x2(o[2], o[3]);
       }
+      FF_TS(3);
       mbar_wait(h_empty, (j & 1) ^ 1);                        // down(j - 1) has read the previous hidden chunk
+      FF_TS(4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                           // 16-byte chunks hf * 4 + i of the row, 128-byte swizzle
         const int phys = (hf * 4 + i) ^ (row_in_tile & 7);
@@ -315,84 +386,95 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_co
       }
       fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) ff_arrive<PAIR>(h_full);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_remote(map_to_rank(smem_u32(h_full), 0));
+        else mbar_arrive(h_full);
+      }
+      FF_TS(5);
     }
-    // ---- final epilogue: this thread's row, columns [192 hf, 192 hf + 192)
+#ifdef TONE_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 64 && g_prof)
+      printf("ff epi chunk12: wait_upacc %lld ld %lld math %lld wait_h %lld store %lld\n", ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2],
+             ts[4] - ts[3], ts[5] - ts[4]);
+#endif
+    // ---- final epilogue.  Phase A (thread = row, columns [192 hf, +192)): scale * (acc + b2) -> fp32 tile X[128][388]
+    // staged over the operand buffers, which are dead once the last MMA has completed.
     mbar_wait(dnacc_full, 0);
+    if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
-    const int c0 = hf * 192;
-    float* rrow = a.r + (size_t)row * D_MODEL + c0;
-    float sx = 0.f, sg = 0.f;
+    float* X = reinterpret_cast<float*>(smem);
+    {
+      const int c0 = hf * 192;
+      const uint32_t xrow = smem_u32(X) + (row_in_tile * Cfg::X_PITCH + c0) * 4;
 #pragma unroll 1
-    for (int cb = 0; cb < 192; cb += 32) {                    // pass 1: x = r + scale (acc + b2) -> TMEM; sums of squares
-      uint32_t acc[32];
-      tmem_ld16_async(dnacc + lane_base + c0 + cb, acc);
-      tmem_ld16_async(dnacc + lane_base + c0 + cb + 16, acc + 16);
-      float4 rr[8];
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(rrow + cb + 4 * i);
-      }
-      tmem_ld_wait();
-      tmem_regs_ready16(acc);
-      tmem_regs_ready16(acc + 16);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = *reinterpret_cast<const float4*>(s_vec + c0 + cb + 4 * i);
-        const float4 g = *reinterpret_cast<const float4*>(s_vec + 384 + c0 + cb + 4 * i);
-        const float rv[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w}, bb[4] = {b.x, b.y, b.z, b.w}, gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float x = valid ? fmaf(a.scale, __uint_as_float(acc[4 * i + k]) + bb[k], rv[k]) : 0.f;
-          acc[4 * i + k] = __float_as_uint(x);
-          sx = fmaf(x, x, sx);
-          const float gx = gg[k] * x;
-          sg = fmaf(gx, gx, sg);
-        }
-      }
-      tmem_st16(dnacc + lane_base + c0 + cb, acc);
-      tmem_st16(dnacc + lane_base + c0 + cb + 16, acc + 16);
-    }
-    tmem_st_wait();
-    s_ssq[(0 * 2 + hf) * 128 + row_in_tile] = sx;
-    s_ssq[(1 * 2 + hf) * 128 + row_in_tile] = sg;
-    bar_epilogue();                                           // both column halves of every row have published their sums
-    const float tx = s_ssq[row_in_tile] + s_ssq[128 + row_in_tile];
-    const float tg = s_ssq[256 + row_in_tile] + s_ssq[384 + row_in_tile];
-    // y = g1 x inv1 (norm_out, in place) ; n = g2 y inv2 with rms(y) from sum (g1 x)^2 * inv1^2
-    const float inv1 = a.g1 ? 1.0f / (sqrtf(tx) * 0.05103103630798288f + 1e-8f) : 1.0f;
-    const float ty = a.g1 ? tg * inv1 * inv1 : tx;
-    const float inv2 = a.g2 ? 1.0f / (sqrtf(ty) * 0.05103103630798288f + 1e-8f) : 1.0f;
-    bf16* nrow = a.n ? a.n + (size_t)row * D_MODEL + c0 : nullptr;
-    bf16* krow = nullptr;
-    if (a.kv && valid) {
-      const int b = row / a.rows_per_stream, t = row - b * a.rows_per_stream;
-      krow = a.kv + ((size_t)a.slots[b] * KV_ROWS_MAX + a.kv_row_off + t) * D_MODEL + c0;
-    }
-#pragma unroll 1
-    for (int cb = 0; cb < 192; cb += 32) {                    // pass 2: write r and the normalised bf16 row
-      uint32_t xr[32];
-      tmem_ld16_async(dnacc + lane_base + c0 + cb, xr);
-      tmem_ld16_async(dnacc + lane_base + c0 + cb + 16, xr + 16);
-      tmem_ld_wait();
-      tmem_regs_ready16(xr);
-      tmem_regs_ready16(xr + 16);
-      if (valid) {
+      for (int cb = 0; cb < 192; cb += 32) {
+        uint32_t acc[32];
+        tmem_ld16_async(dnacc + lane_base + c0 + cb, acc);
+        tmem_ld16_async(dnacc + lane_base + c0 + cb + 16, acc + 16);
+        tmem_ld_wait();
+        tmem_regs_ready16(acc);
+        tmem_regs_ready16(acc + 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 g1v = *reinterpret_cast<const float4*>(s_vec + 384 + c0 + cb + 4 * i);
-          const float4 g2v = *reinterpret_cast<const float4*>(s_vec + 768 + c0 + cb + 4 * i);
-          float4 y;
-          y.x = g1v.x * (__uint_as_float(xr[4 * i]) * inv1);
-          y.y = g1v.y * (__uint_as_float(xr[4 * i + 1]) * inv1);
-          y.z = g1v.z * (__uint_as_float(xr[4 * i + 2]) * inv1);
-          y.w = g1v.w * (__uint_as_float(xr[4 * i + 3]) * inv1);
-          *reinterpret_cast<float4*>(rrow + cb + 4 * i) = y;
-          if (nrow) {
-            const uint2 p = make_uint2(pack_bf16x2(g2v.x * (y.x * inv2), g2v.y * (y.y * inv2)),
-                                       pack_bf16x2(g2v.z * (y.z * inv2), g2v.w * (y.w * inv2)));
-            *reinterpret_cast<uint2*>(nrow + cb + 4 * i) = p;
-            if (krow) *reinterpret_cast<uint2*>(krow + cb + 4 * i) = p;
+          const float4 b = *reinterpret_cast<const float4*>(s_vec + c0 + cb + 4 * i);
+          sts128(xrow + (cb + 4 * i) * 4,
+                 make_float4(a.scale * (__uint_as_float(acc[4 * i]) + b.x), a.scale * (__uint_as_float(acc[4 * i + 1]) + b.y),
+                             a.scale * (__uint_as_float(acc[4 * i + 2]) + b.z), a.scale * (__uint_as_float(acc[4 * i + 3]) + b.w)));
+        }
+      }
+    }
+    bar_epilogue();
+    // Phase B (warp = 16 rows, lanes along the row: every global access is a contiguous 512 / 256 bytes):
+    // x = r + X ; [y = g1 x / (rms(x) + eps) -> r] ; n = g2 y / (rms(y) + eps)
+    {
+      const int ew = warp - 2;
+      Vec384 g1v, g2v;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        g1v.v[i] = *reinterpret_cast<const float4*>(s_vec + 384 + i * 128 + lane * 4);
+        g2v.v[i] = *reinterpret_cast<const float4*>(s_vec + 768 + i * 128 + lane * 4);
+      }
+#pragma unroll 1
+      for (int rg = 0; rg < 16; rg += 4) {
+        float4 x[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                       // four rows of residual in flight
+          const int rt = ew * 16 + rg + k, grow = tile * 128 + rt;
+          if (grow < a.M) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[k][i] = *reinterpret_cast<const float4*>(a.r + (size_t)grow * D_MODEL + i * 128 + lane * 4);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rt = ew * 16 + rg + k, grow = tile * 128 + rt;
+          if (grow >= a.M) continue;                        // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float4 d = lds128(smem_u32(X) + (rt * Cfg::X_PITCH + i * 128 + lane * 4) * 4);
+            x[k][i].x += d.x;
+            x[k][i].y += d.y;
+            x[k][i].z += d.z;
+            x[k][i].w += d.w;
+          }
+          float* rr = a.r + (size_t)grow * D_MODEL;
+          if (a.g1) scale_384(x[k], g1v, rms_inv_384(x[k]));
+#pragma unroll
+          for (int i = 0; i < 3; ++i) *reinterpret_cast<float4*>(rr + i * 128 + lane * 4) = x[k][i];
+          if (a.n) {
+            if (a.g2) scale_384(x[k], g2v, rms_inv_384(x[k]));
+            bf16* nr = a.n + (size_t)grow * D_MODEL;
+            bf16* kr = nullptr;
+            if (a.kv) {
+              const int b = grow / a.rows_per_stream, t = grow - b * a.rows_per_stream;
+              kr = a.kv + ((size_t)a.slots[b] * KV_ROWS_MAX + a.kv_row_off + t) * D_MODEL;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const uint2 p = make_uint2(pack_bf16x2(x[k][i].x, x[k][i].y), pack_bf16x2(x[k][i].z, x[k][i].w));
+              *reinterpret_cast<uint2*>(nr + i * 128 + lane * 4) = p;
+              if (kr) *reinterpret_cast<uint2*>(kr + i * 128 + lane * 4) = p;
+            }
           }
         }
       }

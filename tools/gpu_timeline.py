@@ -11,7 +11,7 @@ os.environ["TONE_B200_LIB"] = os.path.join(ROOT, "t-one_b200", "libtone_b200_pro
 sys.path.insert(0, ROOT)
 tb = importlib.import_module("t-one_b200")
 
-NAMES = {1: "begin_step", 2: "norm", 3: "upsample_norm", 4: "attention", 5: "dwconv", 6: "reduction_dw"}
+NAMES = {1: "begin_step", 2: "norm", 3: "upsample_norm", 4: "attention", 5: "dwconv", 6: "reduction_dw", 7: "ff_fused"}
 KINDS = ["store_f32", "resid", "swiglu", "glu", "conv0", "conv1", "kv", "decoder", "partial", "glu_dw", "vatt"]
 
 
@@ -25,7 +25,8 @@ def name(i):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     graph = int(os.environ.get("GRAPH", "1"))
-    eng = tb.Engine(tb.weights.init_weights(0), max_slots=B, max_batch=B, use_graph=bool(graph))
+    kw = {k: int(v) for k, v in (a.split("=") for a in sys.argv[2:])}     # engine keyword arguments, e.g. lanes=1 fused_ff=3
+    eng = tb.Engine(tb.weights.init_weights(0), max_slots=B, max_batch=B, use_graph=bool(graph), **kw)
     lib = eng._lib
     lib.tone_prof_start.argtypes = [C.c_void_p, C.c_int32]
     lib.tone_prof_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]
@@ -45,7 +46,7 @@ def main():
     per = n // 2
     rec = rec[per:]                      # second step
     t0 = rec[0, 0]
-    lines = [f"# B={B} graph={graph} pdl={os.environ.get('TONE_PDL', '1')}  kernels/step={per}",
+    lines = [f"# B={B} graph={graph} {kw}  kernels/step={per}",
              "# seq name grid start_us dur_us gap_us | cycles: prologue wait first_stage acc_ready total"]
     prev_end = t0
     agg = {}
@@ -68,10 +69,10 @@ def main():
         lines.append(f"#   {nm:22s} {c:4d} {d:9.1f} {g:9.1f} {d / c:7.2f} {g / c:7.2f}")
     out = "\n".join(lines)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    tag = f"timeline_B{B}_g{graph}_pdl{os.environ.get('TONE_PDL', '1')}"
+    tag = f"timeline_B{B}_g{graph}_" + "_".join(f"{k}{v}" for k, v in kw.items())
     with open(os.path.join(ROOT, "gpurun_out", tag + ".txt"), "w") as f:
         f.write(out + "\n")
-    print("\n".join(lines[:60]))
+    print("\n".join(lines[:40]))
     print("...")
     print("\n".join(lines[-16:]))
 
