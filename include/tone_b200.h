@@ -215,6 +215,52 @@ int tone_export_states_triton(tone_engine* e, int32_t n, const int32_t* slots, u
 int tone_import_states_triton(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* cache_last_time,
                               const uint16_t* cache_last_channel, const int64_t* cache_last_chan_len);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stream server: sequence batcher + stepping thread above one engine.  The reference delegates this role to Triton -
+ * `sequence_batching { oldest { max_candidate_sequences 4096 } max_sequence_idle_microseconds 15 s }`
+ * (triton/model/config.pbtxt:26-31) and `dynamic_batching { max_queue_delay_microseconds 10000 }`
+ * (configs/streaming_acoustic/config.pbtxt:35-37).  Here: any number of producer threads push chunks; ONE native
+ * thread owns the engine, forms batches (at most one chunk per stream per step, oldest head-of-queue first, a step is
+ * due when max_batch chunks wait or the oldest has waited max_queue_delay), keeps two tickets in flight
+ * (tone_submit / tone_wait), allocates a slot on a stream's first chunk, releases it after its last chunk or when it
+ * has been idle for idle_timeout, and hands completed batches to tone_server_poll.  All entry points are thread-safe.
+ * While a server exists, the engine must not be used directly. */
+typedef struct tone_server tone_server;
+typedef struct tone_server_config {
+  int32_t max_batch;           /* largest step (<= engine max_batch); 0 = engine max_batch                         */
+  int32_t max_queue_delay_us;  /* batching window; 0 = 10000 (the reference's Triton setting)                      */
+  int32_t idle_timeout_ms;     /* idle streams are closed after this long; 0 = 15000                               */
+  int32_t queue_depth;         /* chunks buffered per stream; 0 = 4                                                */
+  int32_t outputs;             /* TONE_OUT_LOGPROBS and / or TONE_OUT_PHRASES delivered per chunk; 0 = PHRASES     */
+} tone_server_config;
+typedef struct tone_server_stats {
+  int64_t steps, chunks, phrases, streams_opened, streams_closed, streams_reclaimed, rejected;
+  int32_t open_streams, queued_chunks;
+  double mean_batch;
+  double latency_ms_p50, latency_ms_p99, latency_ms_max;   /* push -> results available, per chunk */
+  double queue_ms_p50, queue_ms_p99;                        /* push -> batch formed                 */
+} tone_server_stats;
+/* A finished phrase of a stream (see tone_phrase); text ids are in the batch's text pool. */
+typedef struct tone_stream_phrase {
+  uint64_t stream_id;
+  int32_t start_frame, end_frame, text_offset, text_len;
+} tone_stream_phrase;
+
+int tone_server_create(tone_engine* e, const tone_server_config* cfg, tone_server** out);
+void tone_server_destroy(tone_server* s);
+/* Push n chunks, one per listed stream (a stream may appear once per call): pcm int16 [n][chunk_samples];
+ * flags[i] bit 0 = this is the stream's last chunk (nullable = none).  A stream is opened by its first chunk.
+ * All or nothing: TONE_ENOMEM if a stream's queue is full or no slot is left for a new stream. */
+int tone_server_push(tone_server* s, int32_t n, const uint64_t* stream_ids, const int16_t* pcm, const uint8_t* flags);
+/* Take the next completed batch (steps complete in order).  Waits up to timeout_ms for one; *n_chunks = 0 on time-out.
+ *   stream_ids [max_batch], seq [max_batch] (chunk number within its stream), latency_ms [max_batch]
+ *   logprobs   [max_batch][T][35] or NULL (needs TONE_OUT_LOGPROBS)
+ *   phrases    [phrase_cap] or NULL, text [text_cap] or NULL (need TONE_OUT_PHRASES): finished phrases of the batch */
+int tone_server_poll(tone_server* s, int32_t timeout_ms, int32_t* n_chunks, uint64_t* stream_ids, int32_t* seq,
+                     float* latency_ms, float* logprobs, tone_stream_phrase* phrases, int32_t phrase_cap,
+                     int32_t* n_phrases, uint8_t* text, int32_t text_cap, int32_t* text_len);
+int tone_server_get_stats(tone_server* s, tone_server_stats* out);
+
 /* Debug: run one eager step that also records the residual stream after pre-encode and after
  * every Conformer layer.  taps: host fp32 [1+n_layers][B*frames_out][384] (rows of reduced
  * layers 7..14 occupy the first B*T2 rows).  Not a product path. */

@@ -330,6 +330,8 @@ static const int BN_SWIGLU = 128, BN_RESID = 32, BN_GLU = 64, BN_STORE = 64, BN_
 static const int BIG_M = 2048;
 
 extern "C" const char* tone_last_error(void) { return g_err; }
+// internal: lets server.cu report through the same thread-local buffer
+extern "C" void tone_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
 
 static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceProp& prop);
 

@@ -34,6 +34,7 @@ SYMBOLS = (
     "tone_stage", "tone_step_staged", "tone_fetch", "tone_sync", "tone_fetch_greedy", "tone_step_device",
     "tone_export_states", "tone_import_states", "tone_export_states_triton", "tone_import_states_triton",
     "tone_step_debug", "tone_selftest_gemm", "tone_selftest_phrases",
+    "tone_server_create", "tone_server_destroy", "tone_server_push", "tone_server_poll", "tone_server_get_stats",
 )
 
 
@@ -57,6 +58,22 @@ class TonePhrase(C.Structure):
     _fields_ = [("batch_index", C.c_int32), ("start_frame", C.c_int32), ("end_frame", C.c_int32),
                 ("text_offset", C.c_int32), ("text_len", C.c_int32)]
 
+
+class ToneServerConfig(C.Structure):
+    _fields_ = [("max_batch", C.c_int32), ("max_queue_delay_us", C.c_int32), ("idle_timeout_ms", C.c_int32),
+                ("queue_depth", C.c_int32), ("outputs", C.c_int32)]
+
+
+class ToneServerStats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("chunks", C.c_int64), ("phrases", C.c_int64), ("streams_opened", C.c_int64),
+                ("streams_closed", C.c_int64), ("streams_reclaimed", C.c_int64), ("rejected", C.c_int64),
+                ("open_streams", C.c_int32), ("queued_chunks", C.c_int32), ("mean_batch", C.c_double),
+                ("latency_ms_p50", C.c_double), ("latency_ms_p99", C.c_double), ("latency_ms_max", C.c_double),
+                ("queue_ms_p50", C.c_double), ("queue_ms_p99", C.c_double)]
+
+
+STREAM_PHRASE_DTYPE = np.dtype([("stream_id", "<u8"), ("start_frame", "<i4"), ("end_frame", "<i4"),
+                                ("text_offset", "<i4"), ("text_len", "<i4")])
 
 PHRASE_DTYPE = np.dtype([("batch_index", "<i4"), ("start_frame", "<i4"), ("end_frame", "<i4"),
                          ("text_offset", "<i4"), ("text_len", "<i4")])
@@ -107,8 +124,15 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.tone_step_debug.argtypes = [vp, C.c_int32, i32p, i32p, f32p, i32p, f32p]
     lib.tone_selftest_gemm.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_int32]
     lib.tone_selftest_phrases.argtypes = [vp, C.c_int32, i32p, C.c_int32, i32p, f32p, u8p]
+    u64p = C.POINTER(C.c_uint64)
+    lib.tone_server_create.argtypes = [vp, C.POINTER(ToneServerConfig), C.POINTER(vp)]
+    lib.tone_server_destroy.argtypes = [vp]
+    lib.tone_server_destroy.restype = None
+    lib.tone_server_push.argtypes = [vp, C.c_int32, u64p, i16p, u8p]
+    lib.tone_server_poll.argtypes = [vp, C.c_int32, i32p, u64p, i32p, f32p, f32p, vp, C.c_int32, i32p, u8p, C.c_int32, i32p]
+    lib.tone_server_get_stats.argtypes = [vp, C.POINTER(ToneServerStats)]
     for s in SYMBOLS:
-        if s not in ("tone_destroy", "tone_last_error"):
+        if s not in ("tone_destroy", "tone_last_error", "tone_server_destroy"):
             getattr(lib, s).restype = C.c_int
     if path is None:
         _lib = lib

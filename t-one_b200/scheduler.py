@@ -1,5 +1,10 @@
 """Stream scheduler / sequence batcher above the engine.
 
+Two forms.  :class:`StreamServer` is the serving loop: the native, threaded ``tone_server`` of the C ABI (producers push
+chunks from any thread; one native thread forms batches, keeps two tickets in flight and hands back completed batches).
+:class:`StreamScheduler` is the same batching policy as a small synchronous Python class over ``Engine.step`` - handy for
+tests and for callers that want to drive the steps themselves.
+
 The reference has no scheduler of its own: it delegates batching and per-stream state residency to Triton -
 ``sequence_batching { oldest { max_candidate_sequences 4096 } , max_sequence_idle_microseconds 15 s }``
 (reference: triton/model/config.pbtxt:26-31) and ``dynamic_batching { max_queue_delay_microseconds 10000 }`` with
@@ -121,3 +126,85 @@ class StreamScheduler:
         for sid in dead:
             self.close(sid)
         return dead
+
+
+class StreamServer:
+    """The native stream server (``tone_server_*`` of include/tone_b200.h) above one :class:`Engine`.
+
+    ``push(stream_ids, pcm, last=None)`` is thread-safe and returns at once; ``poll()`` returns the next completed batch
+    as a dict (``stream_ids``, ``seq``, ``latency_ms``, optional ``logprobs`` and ``phrases`` = list of (stream_id,
+    start_frame, end_frame, label ids)); ``stats()`` the served counters and the push -> result latency percentiles.
+    While a server exists the engine must not be stepped directly."""
+
+    def __init__(self, engine, max_batch: int = 0, max_queue_delay_s: float = 0.010, idle_timeout_s: float = 15.0,
+                 queue_depth: int = 4, outputs: Optional[int] = None):
+        from . import model as M
+        self._M, self.engine, self._lib = M, engine, engine._lib
+        self.outputs = M.OUT_PHRASES if outputs is None else outputs
+        cfg = M.ToneServerConfig(max_batch, int(max_queue_delay_s * 1e6), int(idle_timeout_s * 1e3), queue_depth, self.outputs)
+        self._h = M.C.c_void_p()
+        rc = self._lib.tone_server_create(engine._h, M.C.byref(cfg), M.C.byref(self._h))
+        if rc:
+            M._raise(self._lib, rc)
+        mb = max_batch or engine.info.max_batch
+        self._ids = np.empty(mb, dtype=np.uint64)
+        self._seq = np.empty(mb, dtype=np.int32)
+        self._lat = np.empty(mb, dtype=np.float32)
+        self._lp = np.empty((mb, engine.T, 35), dtype=np.float32) if self.outputs & M.OUT_LOGPROBS else None
+        self._ph = np.empty(4 * mb, dtype=M.STREAM_PHRASE_DTYPE)
+        self._text = np.empty(mb * 2304, dtype=np.uint8)
+
+    def push(self, stream_ids, pcm, last=None) -> None:
+        C = self._M.C
+        ids = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+        x = np.ascontiguousarray(pcm, dtype=np.int16)
+        if x.shape != (len(ids), self.engine.chunk_samples):
+            raise ValueError(f"pcm must be int16 ({len(ids)}, {self.engine.chunk_samples}), got {x.shape}")
+        fl = None if last is None else np.ascontiguousarray(last, dtype=np.uint8)
+        rc = self._lib.tone_server_push(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        x.ctypes.data_as(C.POINTER(C.c_int16)),
+                                        fl.ctypes.data_as(C.POINTER(C.c_uint8)) if fl is not None else None)
+        if rc:
+            self._M._raise(self._lib, rc)
+
+    def poll(self, timeout_s: float = 0.1):
+        """-> dict for the next completed batch, or None on time-out."""
+        C = self._M.C
+        n, nph, ntext = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = self._lib.tone_server_poll(
+            self._h, int(timeout_s * 1e3), C.byref(n), self._ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+            self._seq.ctypes.data_as(C.POINTER(C.c_int32)), self._lat.ctypes.data_as(C.POINTER(C.c_float)),
+            self._lp.ctypes.data_as(C.POINTER(C.c_float)) if self._lp is not None else None,
+            self._ph.ctypes.data_as(C.c_void_p), len(self._ph), C.byref(nph),
+            self._text.ctypes.data_as(C.POINTER(C.c_uint8)), len(self._text), C.byref(ntext))
+        if rc:
+            self._M._raise(self._lib, rc)
+        if n.value == 0:
+            return None
+        B = n.value
+        out = {"stream_ids": self._ids[:B].copy(), "seq": self._seq[:B].copy(), "latency_ms": self._lat[:B].copy()}
+        if self._lp is not None:
+            out["logprobs"] = self._lp[:B].copy()
+        if self.outputs & self._M.OUT_PHRASES:
+            text = self._text[: ntext.value]
+            out["phrases"] = [(int(r["stream_id"]), int(r["start_frame"]), int(r["end_frame"]),
+                               text[r["text_offset"]: r["text_offset"] + r["text_len"]].copy()) for r in self._ph[: nph.value]]
+        return out
+
+    def stats(self) -> dict:
+        st = self._M.ToneServerStats()
+        rc = self._lib.tone_server_get_stats(self._h, self._M.C.byref(st))
+        if rc:
+            self._M._raise(self._lib, rc)
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.tone_server_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

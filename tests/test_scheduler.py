@@ -125,3 +125,85 @@ def test_ragged_arrivals_match_isolated_streams(tb, weights):
         assert len(got[sid]) == 5
         assert np.abs(np.stack(got[sid]) - np.stack(want[sid])).max() < 3e-2
     eng.close()
+
+
+@pytest.mark.gpu
+def test_native_stream_server_matches_isolated_streams(tb, weights):
+    """tone_server (native batcher + stepping thread, two tickets in flight): ragged arrivals from two producer threads.
+    Per stream, the log-probs come back in order and equal the stream stepped alone; the phrases are exactly what the
+    reference's splitter + greedy decoder give on those log-probs; end flags close streams; idle streams are reclaimed."""
+    import threading
+    import pipeline_oracle as po
+    C, n_streams, n_chunks = 2400, 37, 9
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=40, max_batch=16)
+    M = tb.model
+    pcm = tb.synth.telephony_pcm(n_streams, C * n_chunks, seed=12)
+    want = {}
+    for sid in range(0, n_streams, 6):                       # isolated runs of a sample of the streams
+        slot = eng.alloc_slots(1)
+        want[sid] = [eng.step(slot, pcm[sid:sid + 1, i * C:(i + 1) * C])[0][0].copy() for i in range(n_chunks)]
+        eng.release_slots(slot)
+    srv = tb.scheduler.StreamServer(eng, max_batch=16, max_queue_delay_s=0.002, idle_timeout_s=0.3, queue_depth=4,
+                                    outputs=M.OUT_LOGPROBS | M.OUT_PHRASES)
+    try:
+        def producer(ids):
+            rng = np.random.default_rng(ids[0])
+            pos = {i: 0 for i in ids}
+            while any(p < n_chunks for p in pos.values()):
+                pick = [i for i in ids if pos[i] < n_chunks and rng.random() < 0.6]
+                if pick:
+                    x = np.stack([pcm[i, pos[i] * C:(pos[i] + 1) * C] for i in pick]).astype(np.int16)
+                    last = np.array([pos[i] == n_chunks - 1 and i % 2 == 0 for i in pick], dtype=np.uint8)   # even streams end
+                    while True:
+                        try:
+                            srv.push(np.array(pick, dtype=np.uint64) + 1000, x, last)
+                            break
+                        except MemoryError:                  # a stream's queue is full: back off
+                            import time
+                            time.sleep(0.001)
+                    for i in pick:
+                        pos[i] += 1
+        th = [threading.Thread(target=producer, args=(list(range(k, n_streams, 2)),)) for k in range(2)]
+        for t in th:
+            t.start()
+        got = {i: [] for i in range(n_streams)}
+        phrases = {i: [] for i in range(n_streams)}
+        total, idle_polls = 0, 0
+        while total < n_streams * n_chunks and idle_polls < 100:
+            r = srv.poll(0.1)
+            if r is None:
+                idle_polls += 1
+                continue
+            assert len(set(r["stream_ids"].tolist())) == len(r["stream_ids"])       # one chunk per stream per step
+            for k, sid in enumerate(r["stream_ids"].tolist()):
+                assert r["seq"][k] == len(got[sid - 1000])                         # per-stream FIFO
+                got[sid - 1000].append(r["logprobs"][k])
+            for sid, a, b, ids in r["phrases"]:
+                phrases[sid - 1000].append(("".join(po.LABELS[t] for t in ids), a, b))
+            total += len(r["stream_ids"])
+        for t in th:
+            t.join()
+        assert total == n_streams * n_chunks
+        for sid, w in want.items():
+            assert np.abs(np.stack(got[sid]) - np.stack(w)).max() < 3e-2           # batch composition changes tile selection
+        for sid in range(n_streams):                                               # phrases: bit-exact on the served log-probs
+            st, ref = None, []
+            for i in range(n_chunks):
+                ph, st = po.split(got[sid][i], st, is_last=(i == n_chunks - 1 and sid % 2 == 0))
+                ref += [(po.greedy(p), a, b) for p, a, b in ph]
+            assert phrases[sid] == ref
+        st = srv.stats()
+        assert st["chunks"] == n_streams * n_chunks and st["streams_opened"] == n_streams
+        assert st["streams_closed"] == (n_streams + 1) // 2                        # the even streams sent an end flag
+        assert 1.0 <= st["mean_batch"] <= 16 and st["latency_ms_p99"] > 0
+        import time
+        time.sleep(0.8)                                                            # odd streams: idle for > 0.3 s
+        st = srv.stats()
+        assert st["open_streams"] == 0 and st["streams_reclaimed"] == n_streams // 2
+        # capacity: 41 new streams do not fit into 40 slots - all or nothing
+        with pytest.raises(MemoryError):
+            srv.push(np.arange(41, dtype=np.uint64), np.zeros((41, C), dtype=np.int16))
+        assert srv.stats()["open_streams"] == 0
+    finally:
+        srv.close()
+        eng.close()
