@@ -44,7 +44,7 @@ struct Stream {
 };
 
 struct Batch {                  // one step, from formation to delivery
-  int32_t ticket = -1, B = 0;
+  int32_t ticket = -1, B = 0;   // B = real chunks (the submitted step may be padded beyond it)
   std::vector<uint64_t> ids;
   std::vector<int32_t> seq, chunk_idx;
   std::vector<Stream*> streams;
@@ -81,6 +81,9 @@ struct tone_server {
   double batch_sum = 0;
   std::vector<float> lat_samples, queue_samples;
   std::string error;                     // first engine failure seen by the worker
+  // Batch-size bucketing: every distinct batch size costs a CUDA-graph capture (milliseconds) at first use, so steps
+  // are padded up to a small set of sizes with scratch streams the server owns (zero PCM, results dropped).
+  std::vector<int32_t> pad_slots;
 };
 
 extern "C" void tone_internal_set_error(const char* msg);   // engine.cu: the buffer behind tone_last_error()
@@ -92,6 +95,16 @@ static int sfail(int code, const char* fmt, ...) {
   va_end(ap);
   tone_internal_set_error(buf);
   return code;
+}
+
+// sizes a step may have: exact up to 16, then multiples of 16 up to 128, then multiples of 64
+static int bucket_size(int B) {
+  if (B <= 16) return B;
+  if (B <= 128) return (B + 15) / 16 * 16;
+  return (B + 63) / 64 * 64;
+}
+static int padded_size(const tone_server* s, int B) {
+  return std::min(std::min(bucket_size(B), B + (int)s->pad_slots.size()), (int)s->cfg.max_batch);
 }
 
 static void release_stream(tone_server* s, Stream* st, bool reclaimed) {   // mutex held; the stream is not in flight
@@ -107,17 +120,19 @@ static void release_stream(tone_server* s, Stream* st, bool reclaimed) {   // mu
 static void finish_batch(tone_server* s, std::unique_ptr<Batch> b) {
   const int T = s->info.frames_out;
   const bool want_lp = s->cfg.outputs & TONE_OUT_LOGPROBS, want_ph = s->cfg.outputs & TONE_OUT_PHRASES;
-  if (want_lp) b->logprobs.resize((size_t)b->B * T * TONE_N_CLASSES);
+  const int Bp = padded_size(s, b->B);   // as submitted
+  if (want_lp) b->logprobs.resize((size_t)Bp * T * TONE_N_CLASSES);
   int rc = tone_wait(s->eng, b->ticket, want_lp ? b->logprobs.data() : nullptr, nullptr, nullptr);
+  if (want_lp) b->logprobs.resize((size_t)b->B * T * TONE_N_CLASSES);
   if (!rc && want_ph) {
     const tone_phrase* ph = nullptr;
     const uint8_t* pool = nullptr;
     int32_t n = 0, npool = 0;
     rc = tone_ticket_phrases(s->eng, b->ticket, &ph, &n, &pool, &npool);
     if (!rc) {
-      b->phrases.resize(n);
       for (int i = 0; i < n; ++i)
-        b->phrases[i] = tone_stream_phrase{b->ids[ph[i].batch_index], ph[i].start_frame, ph[i].end_frame, ph[i].text_offset, ph[i].text_len};
+        if (ph[i].batch_index < b->B)          // padding streams are not anybody's stream
+          b->phrases.push_back(tone_stream_phrase{b->ids[ph[i].batch_index], ph[i].start_frame, ph[i].end_frame, ph[i].text_offset, ph[i].text_len});
       b->text.assign(pool, pool + npool);
     }
   }
@@ -223,16 +238,26 @@ static void worker_main(tone_server* s) {
       int16_t* pcm = nullptr;
       uint8_t* last = nullptr;
       tone_next_staging(s->eng, &sl, &pcm, &last);
-      for (int i = 0; i < b->B; ++i) {
-        sl[i] = b->streams[i]->slot;
-        last[i] = b->last[i];
-        memcpy(pcm + (size_t)i * C, s->pool.data() + (size_t)b->chunk_idx[i] * C, (size_t)C * 2);
-      }
-      int rc = tone_submit(s->eng, b->B, sl, pcm, TONE_PCM_I16, last, s->cfg.outputs, &b->ticket);
+      const int Bp = padded_size(s, b->B);
+      auto fill = [&]() {
+        for (int i = 0; i < b->B; ++i) {
+          sl[i] = b->streams[i]->slot;
+          last[i] = b->last[i];
+          memcpy(pcm + (size_t)i * C, s->pool.data() + (size_t)b->chunk_idx[i] * C, (size_t)C * 2);
+        }
+        for (int i = b->B; i < Bp; ++i) {      // padding: scratch streams, silence
+          sl[i] = s->pad_slots[i - b->B];
+          last[i] = 0;
+          memset(pcm + (size_t)i * C, 0, (size_t)C * 2);
+        }
+      };
+      fill();
+      int rc = tone_submit(s->eng, Bp, sl, pcm, TONE_PCM_I16, last, s->cfg.outputs, &b->ticket);
       if (rc == TONE_ESTATE && pending) {      // both staging sets busy: collect the older ticket first
         finish_batch(s, std::move(pending));
         tone_next_staging(s->eng, &sl, &pcm, &last);
-        rc = tone_submit(s->eng, b->B, sl, pcm, TONE_PCM_I16, last, s->cfg.outputs, &b->ticket);
+        fill();
+        rc = tone_submit(s->eng, Bp, sl, pcm, TONE_PCM_I16, last, s->cfg.outputs, &b->ticket);
       }
       if (rc) {
         std::lock_guard<std::mutex> lk(s->mu);
@@ -270,6 +295,12 @@ extern "C" int tone_server_create(tone_engine* e, const tone_server_config* cfg,
   s->pool.resize(n_chunks * info.chunk_samples);
   s->pool_free.reserve(n_chunks);
   for (size_t i = n_chunks; i-- > 0;) s->pool_free.push_back((int32_t)i);
+  const int n_pad = std::min(63, info.max_slots / 8);
+  if (n_pad > 0) {
+    s->pad_slots.resize(n_pad);
+    rc = tone_alloc_slots(e, n_pad, s->pad_slots.data());
+    if (rc) return rc;
+  }
   s->worker = std::thread(worker_main, s.get());
   *out = s.release();
   return TONE_OK;
@@ -285,6 +316,7 @@ extern "C" void tone_server_destroy(tone_server* s) {
   if (s->worker.joinable()) s->worker.join();
   for (auto& kv : s->streams)
     if (kv.second->slot >= 0) tone_release_slots(s->eng, 1, &kv.second->slot);
+  if (!s->pad_slots.empty()) tone_release_slots(s->eng, (int32_t)s->pad_slots.size(), s->pad_slots.data());
   delete s;
 }
 
@@ -302,9 +334,9 @@ extern "C" int tone_server_push(tone_server* s, int32_t n, const uint64_t* ids, 
     else if (it->second->count >= D) return sfail(TONE_ENOMEM, "stream %llu has %d chunks queued already", (unsigned long long)ids[i], D);
     else if (it->second->ending) return sfail(TONE_ESTATE, "stream %llu already received its last chunk", (unsigned long long)ids[i]);
   }
-  if ((int64_t)s->streams.size() + fresh > s->info.max_slots) {
+  if ((int64_t)s->streams.size() + fresh > s->info.max_slots - (int64_t)s->pad_slots.size()) {
     s->st.rejected += n;
-    return sfail(TONE_ENOMEM, "%d new streams, %zu open of %d slots", fresh, s->streams.size(), s->info.max_slots);
+    return sfail(TONE_ENOMEM, "%d new streams, %zu open of %d slots", fresh, s->streams.size(), s->info.max_slots - (int)s->pad_slots.size());
   }
   if ((size_t)n > s->pool_free.size()) return sfail(TONE_ENOMEM, "chunk pool exhausted");
   for (int i = 0; i < n; ++i) {

@@ -135,7 +135,7 @@ def test_native_stream_server_matches_isolated_streams(tb, weights):
     import threading
     import pipeline_oracle as po
     C, n_streams, n_chunks = 2400, 37, 9
-    eng = tb.Engine(weights, chunk_samples=C, max_slots=40, max_batch=16)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=48, max_batch=16)      # 6 of the 48 slots become the server's padding streams
     M = tb.model
     pcm = tb.synth.telephony_pcm(n_streams, C * n_chunks, seed=12)
     want = {}
@@ -200,9 +200,9 @@ def test_native_stream_server_matches_isolated_streams(tb, weights):
         time.sleep(0.8)                                                            # odd streams: idle for > 0.3 s
         st = srv.stats()
         assert st["open_streams"] == 0 and st["streams_reclaimed"] == n_streams // 2
-        # capacity: 41 new streams do not fit into 40 slots - all or nothing
+        # capacity: 43 new streams do not fit into 48 - 6 slots - all or nothing
         with pytest.raises(MemoryError):
-            srv.push(np.arange(41, dtype=np.uint64), np.zeros((41, C), dtype=np.int16))
+            srv.push(np.arange(43, dtype=np.uint64), np.zeros((43, C), dtype=np.int16))
         assert srv.stats()["open_streams"] == 0
     finally:
         srv.close()
