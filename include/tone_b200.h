@@ -232,6 +232,7 @@ typedef struct tone_server_config {
   int32_t idle_timeout_ms;     /* idle streams are closed after this long; 0 = 15000                               */
   int32_t queue_depth;         /* chunks buffered per stream; 0 = 4                                                */
   int32_t outputs;             /* TONE_OUT_LOGPROBS and / or TONE_OUT_PHRASES delivered per chunk; 0 = PHRASES     */
+  int32_t prewarm;             /* 1 = capture the step graph of every batch-size bucket at create (about a second) */
 } tone_server_config;
 typedef struct tone_server_stats {
   int64_t steps, chunks, phrases, streams_opened, streams_closed, streams_reclaimed, rejected;

@@ -301,6 +301,34 @@ extern "C" int tone_server_create(tone_engine* e, const tone_server_config* cfg,
     rc = tone_alloc_slots(e, n_pad, s->pad_slots.data());
     if (rc) return rc;
   }
+  if (cfg->prewarm) {
+    // One silent step per batch-size bucket on scratch slots, so that no CUDA graph is captured while serving (a
+    // capture costs tens of milliseconds: it would be the p99 of the first seconds).
+    const int nb = std::min(s->cfg.max_batch, info.max_slots - n_pad);
+    std::vector<int32_t> tmp(nb);
+    if ((rc = tone_alloc_slots(e, nb, tmp.data()))) return rc;
+    int last_size = 0;
+    for (int b = 1; b <= nb && !rc; ++b) {
+      const int size = std::min(bucket_size(b), nb);
+      if (size == last_size) continue;
+      last_size = size;
+      int32_t* sl = nullptr;
+      int16_t* pcm = nullptr;
+      uint8_t* last = nullptr;
+      tone_next_staging(e, &sl, &pcm, &last);
+      memcpy(sl, tmp.data(), (size_t)size * 4);
+      memset(pcm, 0, (size_t)size * info.chunk_samples * 2);
+      memset(last, 0, size);
+      int32_t ticket = -1;
+      rc = tone_submit(e, size, sl, pcm, TONE_PCM_I16, last, s->cfg.outputs, &ticket);
+      if (!rc) rc = tone_wait(e, ticket, nullptr, nullptr, nullptr);
+    }
+    tone_release_slots(e, nb, tmp.data());
+    if (rc) {
+      tone_release_slots(e, n_pad, s->pad_slots.data());
+      return rc;
+    }
+  }
   s->worker = std::thread(worker_main, s.get());
   *out = s.release();
   return TONE_OK;

@@ -61,7 +61,7 @@ class TonePhrase(C.Structure):
 
 class ToneServerConfig(C.Structure):
     _fields_ = [("max_batch", C.c_int32), ("max_queue_delay_us", C.c_int32), ("idle_timeout_ms", C.c_int32),
-                ("queue_depth", C.c_int32), ("outputs", C.c_int32)]
+                ("queue_depth", C.c_int32), ("outputs", C.c_int32), ("prewarm", C.c_int32)]
 
 
 class ToneServerStats(C.Structure):

@@ -137,11 +137,11 @@ class StreamServer:
     While a server exists the engine must not be stepped directly."""
 
     def __init__(self, engine, max_batch: int = 0, max_queue_delay_s: float = 0.010, idle_timeout_s: float = 15.0,
-                 queue_depth: int = 4, outputs: Optional[int] = None):
+                 queue_depth: int = 4, outputs: Optional[int] = None, prewarm: bool = False):
         from . import model as M
         self._M, self.engine, self._lib = M, engine, engine._lib
         self.outputs = M.OUT_PHRASES if outputs is None else outputs
-        cfg = M.ToneServerConfig(max_batch, int(max_queue_delay_s * 1e6), int(idle_timeout_s * 1e3), queue_depth, self.outputs)
+        cfg = M.ToneServerConfig(max_batch, int(max_queue_delay_s * 1e6), int(idle_timeout_s * 1e3), queue_depth, self.outputs, int(prewarm))
         self._h = M.C.c_void_p()
         rc = self._lib.tone_server_create(engine._h, M.C.byref(cfg), M.C.byref(self._h))
         if rc:

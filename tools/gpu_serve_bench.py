@@ -22,7 +22,7 @@ tb = importlib.import_module("t-one_b200")
 
 def run(n_streams, max_batch=1024, seconds=4.0, window_ms=10.0, saturate=False, chunk=2400):
     eng = tb.Engine(tb.weights.init_weights(0), chunk_samples=chunk, max_slots=max(n_streams + 64, max_batch), max_batch=max_batch)
-    srv = tb.scheduler.StreamServer(eng, max_batch=max_batch, max_queue_delay_s=window_ms / 1e3, queue_depth=4)
+    srv = tb.scheduler.StreamServer(eng, max_batch=max_batch, max_queue_delay_s=window_ms / 1e3, queue_depth=4, prewarm=True)
     pool = tb.synth.telephony_pcm(256, chunk * 2, seed=7).reshape(512, chunk).astype(np.int16)
     period = chunk / 8000.0
     stop = threading.Event()
