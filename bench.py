@@ -284,6 +284,53 @@ def bench_engine(tb, torch, B, chunk, K, Wm, local, rank, barrier, greedy=True):
     return out
 
 
+def serving_leg(tb, B, chunk, local, barrier, seconds=2.0):
+    """Saturated throughput THROUGH THE STREAM SERVER (tone_server: native batcher thread, 10 ms window, two tickets in
+    flight, device-side phrase splitter): 4 B open streams, a producer thread pushing chunks as fast as the queues take
+    them, a consumer thread polling completed batches.  -> (served audio-s/s, server stats)."""
+    import threading
+    eng = tb.Engine(tb.weights.init_weights(0), chunk_samples=chunk, max_slots=4 * B + 64, max_batch=B, device=local)
+    srv = tb.scheduler.StreamServer(eng, max_batch=B, max_queue_delay_s=0.010, queue_depth=4)
+    pool = tb.synth.telephony_pcm(min(B, 256), chunk * 2, seed=7).reshape(-1, chunk).astype(np.int16)
+    pool = np.ascontiguousarray(np.tile(pool, ((B + len(pool) - 1) // len(pool), 1))[:B])
+    stop, served = threading.Event(), [0]
+
+    def producer():
+        k = 0
+        while not stop.is_set():
+            ids = (np.arange(B, dtype=np.uint64) + (k % 4) * B)
+            try:
+                srv.push(ids, pool)
+                k += 1
+            except MemoryError:
+                time.sleep(0.0005)
+
+    def consumer():
+        while True:
+            r = srv.poll(0.05)
+            if r is None:
+                if stop.is_set():
+                    return
+                continue
+            served[0] += len(r["stream_ids"])
+
+    tp, tc = threading.Thread(target=producer), threading.Thread(target=consumer)
+    tp.start()
+    tc.start()
+    time.sleep(0.7)
+    barrier()
+    c0, t0 = served[0], time.perf_counter()
+    time.sleep(seconds)
+    c1, t1 = served[0], time.perf_counter()
+    stop.set()
+    tp.join()
+    tc.join()
+    st = srv.stats()
+    srv.close()
+    eng.close()
+    return (c1 - c0) * (chunk / 8000.0) / (t1 - t0), st
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -313,6 +360,12 @@ def run_ours(args):
     r = bench_engine(tb, torch, B, chunk, K, Wm, local, rank, barrier)
     clocks = sampler.stop() if rank == 0 else None
     r64 = bench_engine(tb, torch, 64, chunk, max(K, 50), Wm, local, rank, barrier, greedy=False) if B != 64 else None
+    served, served_stats = None, None
+    if not args.no_serving:
+        try:
+            served, served_stats = serving_leg(tb, B, chunk, local, (lambda: dist.barrier()) if world > 1 else (lambda: None))
+        except Exception as ex:  # noqa: BLE001  (the serving leg never takes the headline down with it)
+            served, served_stats = None, {"error": f"{type(ex).__name__}: {ex}"}
 
     def maxr(*vals):
         if world == 1:
@@ -322,6 +375,12 @@ def run_ours(args):
         return [float(v) for v in t]
 
     dev_ms, e2e_s, greedy_s = maxr(r["dev_ms"], r["e2e_s"], r["greedy_s"])
+    if world > 1:
+        t = torch.tensor([served if served is not None else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        served_total = float(t[0])
+    else:
+        served_total = served
     audio_s = world * B * (chunk / 8000.0) * K
     value = audio_s / (dev_ms / 1e3)
     T, info = r["info"]["T"], r["info"]
@@ -374,6 +433,11 @@ def run_ours(args):
                 "sync_latency_ms": {"p50": pct(r64["lat_sync"], 50), "p99": pct(r64["lat_sync"], 99)},
                 "launches_per_step": r64["launches"],
                 "roofline_frac": FLOP_PER_CHUNK[chunk] * 64 / (r64["dev_ms"] / 1e3 / k64) / 1e12 / peaks["tflops"]}
+        if served_stats is not None:
+            line["serving"] = {"value": served_total, "unit": UNIT, "frac_of_device": (served_total or 0.0) / value,
+                               "mode": f"tone_server (native batcher thread, 10 ms window, oldest-first, two tickets in flight, device-side "
+                                       f"phrase splitter), {4 * B} open streams per GPU, saturated producer; sum over ranks",
+                               "mean_batch": served_stats.get("mean_batch"), "error": served_stats.get("error")}
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_throughput(B, chunk, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
@@ -392,6 +456,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2400, choices=[2400, 3200])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-serving", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
