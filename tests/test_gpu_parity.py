@@ -486,3 +486,26 @@ def test_long_stream_stays_finite_and_tracks_oracle(engines, weights, tb):
         assert np.abs(lp[-5:] - ref[-5:]).max() <= LP_TOL
     finally:
         eng.release_slots(slots)
+
+
+def test_results_do_not_depend_on_pool_size_or_slot_position(weights, tb):
+    """Stand-in for a memcheck run (compute-sanitizer is closed on this pool): the same streams stepped in an engine
+    sized exactly for them and in a much larger engine, at the far end of its slot pool, give bit-identical log-probs and
+    state.  An out-of-bounds read that lands in a neighbouring buffer, or any dependence on the pool layout, shows up
+    as a difference."""
+    C, B, n = 2400, 11, 4
+    pcm = tb.synth.telephony_pcm(B, C * n, seed=123)
+    small = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B)
+    big = tb.Engine(weights, chunk_samples=C, max_slots=8 * B + 5, max_batch=B)
+    try:
+        sa = small.alloc_slots(B)
+        junk = big.alloc_slots(7 * B + 5)
+        sb = big.alloc_slots(B)[::-1].copy()
+        la, _ = _stream_engine(small, sa, pcm, C)
+        lb, _ = _stream_engine(big, sb, pcm, C)
+        assert np.array_equal(la, lb)
+        assert np.array_equal(small.export_states(sa), big.export_states(sb))
+        assert not np.abs(big.export_states(junk[:4]).astype(np.float32)).any()      # untouched neighbours stay all-zero
+    finally:
+        small.close()
+        big.close()

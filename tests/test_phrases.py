@@ -215,3 +215,35 @@ def test_greedy_pipeline_on_gpu_matches_full_logprob_path(tb, weights):
         assert all(isinstance(p.text, str) for ph in off for p in ph)
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ property tests
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(runs=st_.lists(st_.tuples(st_.booleans(), st_.integers(1, 70)), min_size=1, max_size=40),
+       T=st_.sampled_from([10, 13]), seed=st_.integers(0, 2 ** 16), flush=st_.booleans())
+def test_state_machine_property(runs, T, seed, flush):
+    """Any alternation of speech / silence runs (lengths around the 20-frame rule and the 3-frame expansion), any chunking,
+    with or without a final flush: the incremental state machine == the reference formulation on full log-probs."""
+    rng = np.random.default_rng(seed)
+    frames = []
+    for speech, n in runs:
+        logits = rng.normal(0, 1.0, size=(n, 35)).astype(np.float32)
+        if speech:
+            logits[np.arange(n), rng.integers(0, 34, n)] += 7.0
+        else:
+            logits[:, 34] += 9.0
+        frames.append(logits - np.log(np.exp(logits).sum(-1, keepdims=True)))
+    lp = np.concatenate(frames)
+    n = len(lp) // T
+    if n == 0:
+        return
+    pm, st = PhraseMachine(), None
+    for i in range(n):
+        c, last = lp[i * T:(i + 1) * T], flush and i == n - 1
+        ph, st = po.split(c, st, is_last=last)
+        want = [(po.greedy(p), a, b) for p, a, b in ph]
+        got = [("".join(LABELS[t] for t in ids), a, b) for ids, a, b in pm.step(c.argmax(-1), c[:, 33:35], is_last=last)]
+        assert got == want and (pm.offset, len(pm.buf)) == (st.offset, len(st.past))
