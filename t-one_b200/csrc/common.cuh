@@ -13,9 +13,18 @@ namespace tone {
 typedef __nv_bfloat16 bf16;
 
 // ----------------------------------------------------------------------------- math
-// x * sigmoid(x) and sigmoid(x) with the approximate reciprocal (2 ulp; the results are rounded to bf16 anyway)
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2) through tanh.approx.f32: ONE MUFU op per element instead of ex2 + rcp (and no range
+// fix-up around ex2), |relative error| < 2^-10 - every result is rounded to bf16 (2^-8) right after.  The epilogues of
+// the gated GEMMs are issue-bound on exactly these instructions.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// ex2 + rcp form (2 ulp): the conv-subsampling epilogues, whose output feeds 16 layers and whose cost is negligible
+__device__ __forceinline__ float silu_exact_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -83,14 +83,7 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_add
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// silu(x) * y with silu(x) = x * (0.5 + 0.5 tanh(x / 2)): one MUFU op per element (tanh.approx, |err| < 1e-3 relative,
-// far below the bf16 rounding of the result)
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float silu_mul(float x, float y) { return x * fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f) * y; }
+__device__ __forceinline__ float silu_mul(float x, float y) { return silu_f(x) * y; }
 
 template <bool PAIR>
 __global__ void __launch_bounds__(FF_THREADS, 1) ff_fused_kernel(const __grid_constant__ CUtensorMap tmA,

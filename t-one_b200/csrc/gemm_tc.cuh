@@ -405,7 +405,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float r[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = silu_f(acc[c + i] * al[i] + be[i]);
+        for (int i = 0; i < 8; ++i) r[i] = silu_exact_f(acc[c + i] * al[i] + be[i]);
         sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
                                                    pack_bf16x2(r[6], r[7])));
       }
@@ -724,7 +724,7 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
         const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float r[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = silu_f(acc[c + i] * al[i] + be[i]);
+        for (int i = 0; i < 8; ++i) r[i] = silu_exact_f(acc[c + i] * al[i] + be[i]);
         sts128u(srow + (cbase + c) * 2, make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
                                                    pack_bf16x2(r[6], r[7])));
       }
