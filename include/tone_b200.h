@@ -87,8 +87,6 @@ typedef struct tone_config {
 
 #define TONE_FLAG_NO_PDL 1         /* launch the kernels of a step without programmatic dependent launch     */
 #define TONE_FLAG_NO_FUSED_VATT 2  /* score-sharing layers: V projection and P.V as two kernels              */
-#define TONE_FLAG_SPLITK_PARTIALS 4 /* feed-forward down projection: split-K partial sums through HBM + a norm  */
-                                   /* kernel instead of the cluster kernel with the reduction over DSMEM      */
 
 /* Shapes a caller needs to size its buffers (tone/onnx_wrapper.py:30-34,
  * configs/streaming_acoustic/config.pbtxt:5-33). */

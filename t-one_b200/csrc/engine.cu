@@ -31,7 +31,6 @@
 #include "kernels.cuh"
 #include "ctc_phrase.cuh"
 #include "ff_fused.cuh"
-#include "ffdown_norm.cuh"
 #include "state_io.cuh"
 
 using namespace tone;
@@ -231,9 +230,6 @@ struct tone_engine {
   // but at 1024 streams per GPU 80 row tiles cannot fill 148 SMs (profiles/r02_fused_ff.md).
   int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
-  // feed-forward down projection + residual + RMSNorms in one cluster kernel with the split-K reduction over distributed
-  // shared memory (ffdown_norm.cuh); false (TONE_FLAG_SPLITK_PARTIALS): split-K partial sums through HBM + norm kernel
-  bool down_norm = true;
   int num_sms = 148;
 };
 
@@ -378,7 +374,6 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->num_sms = prop.multiProcessorCount;
   e->pdl = !(cfg->flags & TONE_FLAG_NO_PDL);
   e->fuse_vatt = !(cfg->flags & TONE_FLAG_NO_FUSED_VATT);
-  e->down_norm = !(cfg->flags & TONE_FLAG_SPLITK_PARTIALS);
   e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
   e->split_k = cfg->split_k;
   if (cfg->fused_ff) e->ff_fused = cfg->fused_ff - 1;
@@ -544,7 +539,6 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_gemm_tc_persist<G_PARTIAL, 1, false>()));
   CK((configure_ff_fused<false>()));
   CK((configure_ff_fused<true>()));
-  CK(configure_ffdown_norm());
   e->persist_ctas = e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
@@ -1161,41 +1155,6 @@ static int run_ff_fused(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, 
   return 0;
 }
 
-// Feed-forward as two kernels: the up projection + SwiGLU GEMM, then ffdown_norm_kernel (down projection with the split-K
-// reduction over distributed shared memory, residual add and the RMSNorms that follow).
-static int run_ff_down_norm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, float* r, const WeightMat& up,
-                            const float* up_b, const WeightMat& down, const float* down_b, int ss_tiles, const float* g1,
-                            const float* g2, bf16* n_out, bf16* kv = nullptr, int rows_per_stream = 1, int kv_row_off = 0) {
-  const int mt = (M + 127) / 128;
-  GemmArgs u = dense_args(M, D_MODEL, ss_tiles ? ln.rb : ln.n, ln.h, D_FF, up_b, 1.f);
-  if (ss_tiles) {
-    u.ss = ln.ss;
-    u.ss_ld = 12;
-    u.ss_tiles = ss_tiles;
-  }
-  RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ss_tiles ? ln.m_rb : ln.m_n, up, u, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
-  FfArgs a;
-  memset(&a, 0, sizeof(a));
-  a.M = M;
-  a.down_bias = down_b;
-  a.r = r;
-  a.scale = 0.5f;
-  a.g1 = g1;
-  a.g2 = g2;
-  a.n = n_out;
-  a.kv = kv;
-  a.slots = ln.slots;
-  a.rows_per_stream = rows_per_stream;
-  a.kv_row_off = kv_row_off;
-  int sk = 8;                                   // K split = cluster size: as many CTAs as fit the GPU once
-  while (sk > 1 && mt * sk > e->num_sms) sk >>= 1;
-  if (e->split_k) sk = e->split_k == 3 ? 2 : (e->split_k > 8 ? 8 : e->split_k);
-  cudaError_t err = launch_ffdown_norm(st, ln.m_h, down.map, a, mt, sk, e->pdl);
-  e->launches++;
-  if (err != cudaSuccess) return fail(TONE_ECUDA, "feed-forward down + norm launch: %s", cudaGetErrorString(err));
-  return 0;
-}
-
 // r += A W^T + b through the tensor cores; also emits bf16(r) and the per-tile row sums of squares that let the next
 // GEMM apply the following RMSNorm as a row scale.  Returns the number of ss tiles through *ss_tiles.
 static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const bf16* A,
@@ -1312,18 +1271,11 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     const int mt = (M + 127) / 128;
     PartIn ff;
     const bool fused_ff = use_ff_fused(e, M);
-    const bool down_norm = !fused_ff && e->cfg.gemm_impl == 0 && e->down_norm;
-    const bool no_norm_kernel = fused_ff || down_norm;
     if (fused_ff) {   // feed-forward 1 + residual + norm_self_att (+ cache-row scatter of layers 14 / 15) in one kernel
       if (l < 14) RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n));
       else
         RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n,
                         l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
-    } else if (down_norm) {
-      if (l < 14) RC(run_ff_down_norm(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n));
-      else
-        RC(run_ff_down_norm(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n,
-                            l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
     } else {
       RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
     }
@@ -1339,7 +1291,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     at.recompute = RECOMPUTE[l] ? 1 : 0;
     bool fused_att = false;
     if (l < 14) {
-      if (!no_norm_kernel) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
@@ -1383,7 +1335,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     } else {
       const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
       bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
-      if (!no_norm_kernel) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
       float* qbuf = ln.qkv;
       float* kvout = ln.qkv + (size_t)e->rows_alloc * D_MODEL;
       GemmArgs a = dense_args(M, D_MODEL, ln.n, qbuf, D_MODEL, L.q_b, 1.f);
@@ -1448,18 +1400,17 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     }
     RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles));
     // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer
-    if (no_norm_kernel) {   // feed-forward 2 + residual + norm_out + the next layer's first norm without a norm kernel
+    if (fused_ff) {   // feed-forward 2 + residual + norm_out + the next layer's first norm in one kernel
       const float* g1 = l == 14 ? nullptr : L.n_out;
       const float* g2 = (l == 6 || l >= 14) ? nullptr : e->L[l + 1].n_ff1;
       bf16* n_out = (l == 6 || l == 14) ? nullptr : ln.n;
-      if (fused_ff) RC(run_ff_fused(e, ln, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, ss_tiles, g1, g2, n_out));
-      else RC(run_ff_down_norm(e, ln, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, ss_tiles, g1, g2, n_out));
+      RC(run_ff_fused(e, ln, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, ss_tiles, g1, g2, n_out));
       ff = PartIn();
     } else {
       RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff, ss_tiles));
     }
     if (l == 6) {
-      if (!no_norm_kernel) RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{ln.r_full, e->st_red, ln.slots, e->red_dw_w, e->red_dw_b, ln.m_red, T, T2};
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
@@ -1475,10 +1426,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       else KLAUNCH(launch_kernel(upsample_norm_kernel<2>, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, ln.r_full, B * T));
     } else if (l == 15) {
-      if (!no_norm_kernel) RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     } else {
-      if (!no_norm_kernel) RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
+      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     }
   }

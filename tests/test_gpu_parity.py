@@ -520,31 +520,3 @@ def test_results_do_not_depend_on_pool_size_or_slot_position(weights, tb):
     finally:
         small.close()
         big.close()
-
-
-@pytest.mark.parametrize("C,B,split_k", [(2400, 7, 0), (3200, 300, 0), (2400, 64, 2), (2400, 64, 4), (2400, 130, 1)])
-def test_feed_forward_down_variants_match_oracle(weights, tb, C, B, split_k):
-    """The default feed-forward down projection is the cluster kernel (split-K reduced over distributed shared memory,
-    residual + RMSNorms fused; cluster sizes 8 / 4 / 2 / 1 chosen by batch size or forced through split_k); the older
-    form - split-K partial sums through HBM + norm kernel - stays selectable (TONE_FLAG_SPLITK_PARTIALS).  Both must
-    match the oracle, and each other closely."""
-    n = 3
-    W = orc.to_torch(weights)
-    pcm = tb.synth.telephony_pcm(min(B, 8), C * n, seed=900 + B)
-    idx = np.arange(B) % pcm.shape[0]
-    ref, st = _stream_oracle(W, pcm, C)
-    outs = []
-    for flags in (0, tb.model.FLAG_SPLITK_PARTIALS):
-        eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, flags=flags, split_k=split_k)
-        try:
-            slots = eng.alloc_slots(B)
-            lp, tk = _stream_engine(eng, slots, np.ascontiguousarray(pcm[idx]), C)
-            assert _lp_close(lp, ref[:, idx])
-            _check_tokens(tk, ref[:, idx])
-            flat_ref = orc.pack_state(st).astype(np.float32)
-            got = eng.export_states(slots[: min(B, 16)]).astype(np.float32)
-            assert np.abs(got - flat_ref[idx[: min(B, 16)]]).max() <= ST_TOL
-            outs.append(lp)
-        finally:
-            eng.close()
-    assert np.abs(outs[0] - outs[1]).max() < 4e-2
