@@ -2,8 +2,8 @@
 
 The numbers are the `configs/streaming_acoustic` architecture, i.e. the defaults of
 the reference's ``ToneConfig`` (reference: tone/training/model_wrapper.py:27-115).
-They decide every shape on the hot path; the C side mirrors this struct as
-``tone_arch_t`` (include/tone_b200.h).
+They decide every shape on the hot path; the C side holds the same numbers as compile-time constants
+(t-one_b200/csrc/kernels.cuh, engine.cu) and checks the shapes of the loaded weights against them.
 """
 from __future__ import annotations
 
