@@ -1525,7 +1525,7 @@ static int launch_step(tone_engine* e, int set, int B, cudaStream_t st, int mode
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) return fail(TONE_ECUDA, "graph instantiate: %s", cudaGetErrorString(ie));
     if (e->graphs.size() >= 64) {   // bound the cache: a dynamic batcher can name many batch sizes
-      CK(cudaStreamSynchronize(e->stream));
+      CK(cudaDeviceSynchronize());   // a graph may still be running on a caller's stream
       for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
       e->graphs.clear();
     }
@@ -1570,6 +1570,8 @@ static inline tone_engine::IoSet& legacy_set(tone_engine* e) { return e->io[tone
 extern "C" int tone_next_staging(tone_engine* e, int32_t** slots, int16_t** pcm16, uint8_t** is_last) {
   if (!e) return fail(TONE_EINVAL, "null engine");
   tone_engine::IoSet& io = e->io[e->next_ticket % tone_engine::PIPE];
+  if (io.busy)   // its H2D copies may still be reading the pinned buffers
+    return fail(TONE_ESTATE, "ticket %d of the next staging set has not been waited for", io.ticket);
   if (slots) *slots = io.p_slots;
   if (pcm16) *pcm16 = io.p_pcm;
   if (is_last) *is_last = io.p_last;

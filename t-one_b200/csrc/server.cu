@@ -18,6 +18,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/tone_b200.h"
@@ -36,6 +37,7 @@ struct Stream {
   int32_t head = 0, count = 0; // ring of queued chunks (indices into the chunk pool)
   int32_t seq = 0;             // chunks stepped so far
   bool ending = false;         // the last chunk has been pushed
+  uint64_t push_mark = 0;      // generation of the last tone_server_push that named this stream (duplicate detection)
   int32_t in_flight = 0;       // tickets in flight that contain a chunk of this stream
   Clock::time_point last_active;
   std::vector<int32_t> ring;   // [queue_depth] chunk-pool indices
@@ -81,6 +83,8 @@ struct tone_server {
   double batch_sum = 0;
   std::vector<float> lat_samples, queue_samples;
   std::string error;                     // first engine failure seen by the worker
+  uint64_t push_gen = 0;
+  std::unordered_set<uint64_t> fresh_ids;
   // Batch-size bucketing: every distinct batch size costs a CUDA-graph capture (milliseconds) at first use, so steps
   // are padded up to a small set of sizes with scratch streams the server owns (zero PCM, results dropped).
   std::vector<int32_t> pad_slots;
@@ -354,13 +358,22 @@ extern "C" int tone_server_push(tone_server* s, int32_t n, const uint64_t* ids, 
   const auto now = Clock::now();
   std::lock_guard<std::mutex> lk(s->mu);
   if (!s->error.empty()) return sfail(TONE_ECUDA, "server stopped: %s", s->error.c_str());
-  // all or nothing: check capacity first
+  // all or nothing: check duplicates and capacity first
   int fresh = 0;
+  ++s->push_gen;
+  s->fresh_ids.clear();
   for (int i = 0; i < n; ++i) {
     auto it = s->streams.find(ids[i]);
-    if (it == s->streams.end()) ++fresh;
-    else if (it->second->count >= D) return sfail(TONE_ENOMEM, "stream %llu has %d chunks queued already", (unsigned long long)ids[i], D);
-    else if (it->second->ending) return sfail(TONE_ESTATE, "stream %llu already received its last chunk", (unsigned long long)ids[i]);
+    if (it == s->streams.end()) {
+      if (!s->fresh_ids.insert(ids[i]).second) return sfail(TONE_EINVAL, "stream %llu appears twice in one push", (unsigned long long)ids[i]);
+      ++fresh;
+      continue;
+    }
+    Stream* st = it->second.get();
+    if (st->push_mark == s->push_gen) return sfail(TONE_EINVAL, "stream %llu appears twice in one push", (unsigned long long)ids[i]);
+    st->push_mark = s->push_gen;
+    if (st->count >= D) return sfail(TONE_ENOMEM, "stream %llu has %d chunks queued already", (unsigned long long)ids[i], D);
+    if (st->ending) return sfail(TONE_ESTATE, "stream %llu already received its last chunk", (unsigned long long)ids[i]);
   }
   if ((int64_t)s->streams.size() + fresh > s->info.max_slots - (int64_t)s->pad_slots.size()) {
     s->st.rejected += n;
@@ -378,7 +391,6 @@ extern "C" int tone_server_push(tone_server* s, int32_t n, const uint64_t* ids, 
       s->st.streams_opened++;
     }
     Stream* st = up.get();
-    if (st->count >= D) return sfail(TONE_EINVAL, "stream %llu appears twice in one push", (unsigned long long)ids[i]);
     const int32_t ci = s->pool_free.back();
     s->pool_free.pop_back();
     memcpy(s->pool.data() + (size_t)ci * C, pcm + (size_t)i * C, (size_t)C * 2);
