@@ -1306,7 +1306,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
         at.q_ln_b = L.qln_b;
         at.k_ln_w = L.kln_w;
         at.k_ln_b = L.kln_b;
-      } else if (e->cfg.gemm_impl == 0 && e->fuse_vatt && M < BIG_M) {
+      } else if (e->cfg.gemm_impl == 0 && e->fuse_vatt) {
         // score-sharing layer: ctx = P (n Wv^T + bv) per head in ONE kernel; tiles = whole streams x one head
         GemmArgs a;
         memset(&a, 0, sizeof(a));

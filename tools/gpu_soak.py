@@ -4,7 +4,7 @@ Runs `--steps` consecutive chunks per stream (9000 = 1 hour of audio per stream)
   * log-probs and the exported state must be finite, probabilities must sum to one;
   * ORACLE CHECK: the carried state of `--sample` streams is exported (flat fp16 wire format), the oracle is re-seeded from
     exactly that state (unpack_state) and steps the next chunk; the engine's log-probs of that chunk must agree within
-    the stated tolerance (0.06).  Errors cannot hide behind a drifting state: every check restarts the oracle from the
+    the stated tolerance (0.06 above a reference log-prob of -6, 0.08 above -10, 0.10 everywhere).  Errors cannot hide behind a drifting state: every check restarts the oracle from the
     engine's own state at that point of the hour.
 The first `--oracle-steps` steps are also compared chunk by chunk from the zero state.
 Usage: python tools/gpu_soak.py [--steps 9000] [--out gpurun_out/soak.json]"""
@@ -76,20 +76,21 @@ def main():
         done += 1
         ref, _ = orc.step(W, torch.from_numpy(chunk[pick].astype(np.int32)), orc.unpack_state(state))
         d = np.abs(lp[pick] - ref.numpy())
-        err = float(d[ref.numpy() > -10.0].max())            # stated tolerance: 0.06 above a reference log-prob of -10 ...
-        err_tail = float(d.max())                            # ... 0.10 for the classes below
-        worst = max(worst, err)
+        err = float(d[ref.numpy() > -6.0].max())             # stated tolerance: 0.06 above a reference log-prob of -6,
+        err_mid = float(d[ref.numpy() > -10.0].max())         # 0.08 above -10,
+        err_tail = float(d.max())                            # 0.10 everywhere
+        worst = max(worst, err_tail)
         top2 = np.sort(ref.numpy(), axis=-1)[..., -2:]
         decided = (top2[..., 1] - top2[..., 0]) > LP_TOL
         tok_ok = bool((tk[pick][decided] == ref.numpy().argmax(-1)[decided]).all())
         st32 = state.astype(np.float32)
         ok = bool(np.isfinite(lp).all() and np.isfinite(st32).all())
-        checks.append({"step": done, "finite": ok, "streams_checked": pick.tolist(), "max_abs_dlogprob_vs_oracle": err, "max_abs_dlogprob_tail": err_tail,
+        checks.append({"step": done, "finite": ok, "streams_checked": pick.tolist(), "max_abs_dlogprob_vs_oracle": err, "max_abs_dlogprob_above_m10": err_mid, "max_abs_dlogprob_tail": err_tail,
                        "tokens_equal_above_margin": tok_ok, "logprob_min": float(lp.min()),
                        "state_absmax": float(np.abs(st32).max()), "prob_sum_err": float(np.abs(np.exp(lp).sum(-1) - 1).max())})
         print(checks[-1], flush=True)
         assert ok, "non-finite values"
-        assert err <= LP_TOL and err_tail <= 0.10 and tok_ok, f"oracle check failed at step {done}: {err}"
+        assert err <= LP_TOL and err_mid <= 0.08 and err_tail <= 0.10 and tok_ok, f"oracle check failed at step {done}: {err}"
     steps_timed = sum(min(a.check_every, a.steps - s) - 1 for s in range(a.oracle_steps, a.steps, a.check_every))
     audio_s = B * C / 8000.0 * steps_timed
     res = {"streams": B, "chunk_samples": C, "steps_per_stream": a.steps, "audio_hours_total": B * C / 8000.0 * a.steps / 3600,
