@@ -208,7 +208,7 @@ struct tone_engine {
     float* aux_out;
   };
   std::vector<Lane> lanes;
-  int n_lanes = 2, lane_min_batch = 256;   // measured: lanes only pay once kernels are throughput bound (B >= 512)
+  int n_lanes = 2, lane_min_batch = 384;   // measured: lanes pay from ~768 streams (512 streams: 1.815 ms in one lane, 1.860 in two)
   cudaEvent_t fork_ev = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined step
   cudaStream_t s_cap = nullptr;                   // graph capture happens on a stream of its own
