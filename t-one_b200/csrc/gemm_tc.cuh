@@ -1246,7 +1246,12 @@ inline cudaError_t launch_gemm_tc_persist(cudaStream_t st, const CUtensorMap& tm
                                           int m_tiles, int n_tiles, bool pdl, int ctas) {
   const int tiles_y = n_tiles / NSUB;
   const int ntiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * tiles_y;
-  int grid = PAIR ? 2 * std::min(ntiles, ctas / 2) : std::min(ntiles, ctas);
+  // as few CTAs (CTA pairs) as reach the same number of rounds: 480 tiles on 148 SMs take 4 rounds whether 148 or 120 CTAs
+  // walk them, and the 28 SMs left free serve the other lane's kernels meanwhile
+  const int units_max = PAIR ? ctas / 2 : ctas;
+  const int rounds = (ntiles + units_max - 1) / units_max;
+  const int units = (ntiles + rounds - 1) / rounds;
+  int grid = PAIR ? 2 * units : units;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
