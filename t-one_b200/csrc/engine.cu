@@ -523,6 +523,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_gemm_tc<G_CONV0, BN_CONV>()));
   CK((configure_gemm_tc<G_CONV1, BN_CONV>()));
   CK((configure_gemm_tc<G_KV, BN_KV>()));
+  CK((configure_gemm_tc<G_KV, 128>()));
   CK((configure_gemm_tc<G_DECODER, DEC_PAD>()));
   CK((configure_gemm_tc<G_PARTIAL, BN_PART>()));
   CK((configure_gemm_tc<G_VATT, D_HEAD>()));
@@ -541,7 +542,8 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_ff_fused<true>()));
   e->persist_ctas = e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
-  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_V_SMEM));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine streams are non-blocking
   return TONE_OK;
 }
@@ -1213,9 +1215,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     a.F = F;
     a.T = T;
     a.T2 = T2;
+    a.B = B;
     const int n_mt = (F + 15) / 16, UH = ((16 * n_mt * HOP + HOP + 16) + 7) & ~7;
-    const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4;
-    KLAUNCH(launch_kernel(begin_step_kernel, dim3(B), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
+    const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + ROLL_BYTES + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4;
+    KLAUNCH(launch_kernel(begin_step_kernel, dim3(std::min(B, e->num_sms)), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
   }
   {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels
     GemmArgs a;
@@ -1354,8 +1357,12 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       k.A = kvbuf;
       k.lda = D_MODEL;
       k.a_slot_stride = KV_ROWS_MAX * D_MODEL;
-      RC((gemm<G_KV, BN_KV>(e, st, l == 14 ? e->m_kv14 : e->m_kv15, L.kv, k, (B + k.G - 1) / k.G, 2 * D_MODEL / BN_KV,
-                            B * k.R, 2 * D_MODEL, l == 14 ? &e->w_kv14 : &e->w_kv15)));
+      if (B * k.R >= BIG_M)   // large batch: 128-wide tiles halve the re-reads of the gathered A rows
+        RC((gemm<G_KV, 128>(e, st, l == 14 ? e->m_kv14 : e->m_kv15, L.kv, k, (B + k.G - 1) / k.G, 2 * D_MODEL / 128,
+                            B * k.R, 2 * D_MODEL, l == 14 ? &e->w_kv14 : &e->w_kv15, 1, true)));
+      else
+        RC((gemm<G_KV, BN_KV>(e, st, l == 14 ? e->m_kv14 : e->m_kv15, L.kv, k, (B + k.G - 1) / k.G, 2 * D_MODEL / BN_KV,
+                              B * k.R, 2 * D_MODEL, l == 14 ? &e->w_kv14 : &e->w_kv15)));
       at.S = S;
       at.Tk = S + Tl;
       at.q = qbuf;
@@ -1370,7 +1377,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.mask_mode = (l == 14) ? 2 : 1;
     }
     if (fused_att) {
-    } else if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), 0, st, e->pdl, at));
+    } else if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), ATT_V_SMEM, st, e->pdl, at));
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
     RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));

@@ -50,6 +50,7 @@ struct BeginArgs {
   const float* mel_w;        // [nnz]
   const float* pre_norm_g;   // [64]
   int C, F, T, T2;
+  int B;                     // streams in the batch
 };
 
 // One CTA per stream, 352 threads (11 warps).  The framed DFT runs on the tensor cores as an fp16 GEMM with fp32
@@ -67,6 +68,24 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Persistent: grid = min(B, SM count) CTAs, each walks streams b = blockIdx.x, + gridDim.x, ... with the DFT basis
+// staged ONCE.  The start-of-step rolls of the large per-stream caches (x1 8 rows, layer-15 / layer-14 attention rows:
+// 57 KB per stream, contiguous blocks) go through a shared-memory staging buffer as bulk async copies issued by one
+// thread: the loads of stream i travel under its front-end arithmetic and the stores drain under stream i + 1's.
+constexpr int ROLL_X1_BYTES = SUB2_ROWS * X1_ROW * 2;            // 22,528
+constexpr int ROLL_KV15_BYTES = MHSA_S * D_MODEL * 2;            // 23,040
+constexpr int ROLL_KV14_BYTES = (MHSA_S / 2) * D_MODEL * 2;      // 11,520
+constexpr int ROLL_BYTES = ROLL_X1_BYTES + ROLL_KV15_BYTES + ROLL_KV14_BYTES;
+
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginArgs a) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   PROF_DECL();
@@ -76,20 +95,23 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   const int n_mt = (F + 15) / 16;                       // frame tiles of 16
   const int UH = 16 * n_mt * HOP + HOP + 16;            // halfs: frames of the padded tiles stay in bounds
   __half* basisS = reinterpret_cast<__half*>(sm_raw);   // [2][BASIS_N][BASIS_LD] hi, lo
-  __half* uh = basisS + 2 * BASIS_N * BASIS_LD;         // [UH] carried 80 samples + chunk, zero tail
+  unsigned char* rollS = sm_raw + 2 * BASIS_N * BASIS_LD * 2;   // [ROLL_BYTES] x1 | kv15 | kv14 rows in flight
+  __half* uh = reinterpret_cast<__half*>(rollS + ROLL_BYTES);   // [UH] carried 80 samples + chunk, zero tail
   float* spec = reinterpret_cast<float*>(uh + ((UH + 7) & ~7));   // [F][162]
   float* featS = spec + F * 162;                        // [F][64]
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   // constant basis -> smem by ONE bulk async copy (113 KB), issued before the PDL wait and awaited just before the DFT;
   // the mel filterbank (CSR, ~1 KB) is staged the same way so that the mel loop does not chase indices in global memory
-  __shared__ uint64_t basis_bar;
+  __shared__ uint64_t basis_bar, roll_bar;
   __shared__ int mel_startS[N_MELS + 1];
   __shared__ unsigned char mel_binS[256];
   __shared__ float mel_wS[256];
   constexpr uint32_t BASIS_BYTES = 2 * BASIS_N * BASIS_LD * 2;
-  static_assert(BASIS_BYTES % 16 == 0, "bulk copy granularity");
+  static_assert(BASIS_BYTES % 16 == 0 && ROLL_X1_BYTES % 16 == 0 && ROLL_KV15_BYTES % 16 == 0 && ROLL_KV14_BYTES % 16 == 0,
+                "bulk copy granularity");
   if (tid == 0) {
     mbar_init(&basis_bar, 1);
+    mbar_init(&roll_bar, 1);
     fence_mbar_init();
     mbar_expect_tx(&basis_bar, BASIS_BYTES);
     bulk_load_1d(basisS, a.basis, BASIS_BYTES, &basis_bar);
@@ -102,40 +124,29 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
       mel_wS[i] = a.mel_w[i];
     }
   }
+  __syncthreads();                                       // barrier inits visible before anybody waits on them
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
-  const int slot = a.slots[b];
 
+  int iter = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
+  const int slot = a.slots[b];
+  bf16* x1p = a.x1 + (size_t)slot * X1_ROWS_MAX * X1_ROW;
+  bf16* k15p = a.kv15 + (size_t)slot * KV_ROWS_MAX * D_MODEL;
+  bf16* k14p = a.kv14 + (size_t)slot * KV_ROWS_MAX * D_MODEL;
   // ---- start-of-step cache rolls: the last rows of [cache | previous new rows] become the cache
+  if (tid == 0) {
+    // x1 rows [F, F+8) -> [0, 8); layer-15 rows [T, T+30) -> [0, 30); layer-14 rows [T2, T2+15) -> [0, 15)
+    if (iter) bulk_wait_read0();                         // the previous stream's stores have left the staging buffer
+    mbar_expect_tx(&roll_bar, ROLL_BYTES);
+    bulk_load_1d(rollS, x1p + (size_t)F * X1_ROW, ROLL_X1_BYTES, &roll_bar);
+    bulk_load_1d(rollS + ROLL_X1_BYTES, k15p + (size_t)a.T * D_MODEL, ROLL_KV15_BYTES, &roll_bar);
+    bulk_load_1d(rollS + ROLL_X1_BYTES + ROLL_KV15_BYTES, k14p + (size_t)a.T2 * D_MODEL, ROLL_KV14_BYTES, &roll_bar);
+  }
   {
-    // feature rows [F, F+10) -> [0, 10)  (80 x 16 B), x1 rows [F, F+8) -> [0, 8) (1408 x 16 B): disjoint ranges
+    // feature rows [F, F+10) -> [0, 10)  (80 x 16 B): disjoint ranges
     uint4* f4 = reinterpret_cast<uint4*>(a.feat + (size_t)slot * FEAT_ROWS_MAX * N_MELS);
     if (tid < SUB1_ROWS * N_MELS / 8) f4[tid] = f4[F * N_MELS / 8 + tid];
-    uint4* x4 = reinterpret_cast<uint4*>(a.x1 + (size_t)slot * X1_ROWS_MAX * X1_ROW);
-    {
-      uint4 t[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (tid + q * BEGIN_THREADS < SUB2_ROWS * X1_ROW / 8) t[q] = x4[F * X1_ROW / 8 + tid + q * BEGIN_THREADS];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (tid + q * BEGIN_THREADS < SUB2_ROWS * X1_ROW / 8) x4[tid + q * BEGIN_THREADS] = t[q];
-    }
-    // attention caches overlap their source: load everything, barrier, store
-    uint4* k15 = reinterpret_cast<uint4*>(a.kv15 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
-    uint4* k14 = reinterpret_cast<uint4*>(a.kv14 + (size_t)slot * KV_ROWS_MAX * D_MODEL);
-    constexpr int RV = D_MODEL / 8;       // uint4 per row
-    uint4 r15[5], r14[3];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int idx = tid + i * BEGIN_THREADS;
-      if (idx < MHSA_S * RV) r15[i] = k15[a.T * RV + idx];
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      int idx = tid + i * BEGIN_THREADS;
-      if (idx < (MHSA_S / 2) * RV) r14[i] = k14[a.T2 * RV + idx];
-    }
     // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
     __half* pre = a.pre + (size_t)slot * HOP;
     const int* pcm32 = reinterpret_cast<const int*>(a.pcm) + (size_t)b * C;
@@ -150,16 +161,6 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int idx = tid + i * BEGIN_THREADS;
-      if (idx < MHSA_S * RV) k15[idx] = r15[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      int idx = tid + i * BEGIN_THREADS;
-      if (idx < (MHSA_S / 2) * RV) k14[idx] = r14[i];
-    }
     if (tid == 0) {
       int len = a.mhsa_len[slot];
       a.len_in[b] = len;
@@ -231,6 +232,14 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     }
     featS[i] = logf(e + 5.9604644775390625e-08f);   // 2^-24
   }
+  // the rolled rows have landed in the staging buffer: send them to the front of their buffers
+  if (tid == 0) {
+    mbar_wait(&roll_bar, iter & 1);
+    bulk_store_1d(x1p, rollS, ROLL_X1_BYTES);
+    bulk_store_1d(k15p, rollS + ROLL_X1_BYTES, ROLL_KV15_BYTES);
+    bulk_store_1d(k14p, rollS + ROLL_X1_BYTES + ROLL_KV15_BYTES, ROLL_KV14_BYTES);
+    bulk_commit();
+  }
   __syncthreads();
   if (threadIdx.x == 0) PROF_MARK(4);
   // ---- RMSNorm(64) per frame (conformer_blocks.py:632, submodules.py:45-54), bf16 rows behind the 10 cached rows
@@ -243,6 +252,8 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     frow[f * N_MELS + lane] = __float2bfloat16(a.pre_norm_g[lane] * (x0 * inv));
     frow[f * N_MELS + 32 + lane] = __float2bfloat16(a.pre_norm_g[32 + lane] * (x1 * inv));
   }
+  }
+  if (tid == 0) bulk_wait0();                            // all rolled rows are in global memory before the grid completes
   PROF_END();
 }
 
@@ -515,6 +526,13 @@ constexpr int ATT_THREADS_REC = 256;
 constexpr int ATT_HEADS_REC = 4;            // heads per CTA in the recompute instantiation (grid.y = 2)
 constexpr int ATT_THREADS = D_MODEL;       // 384
 constexpr int ATT_TK = MHSA_S + MAX_T;     // 43
+constexpr int ATT_V_SMEM = ATT_TK * ATT_HEADS_REC * D_HEAD * 4;   // 33,024 B: V tile of the recompute instantiation
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool RECOMPUTE>
 __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) attention_kernel(const AttnArgs a) {
@@ -524,6 +542,9 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
   // query rows as [t][d / 4][head] float4: the heads of a quarter-warp read consecutive 16 B words (no conflicts)
   __shared__ float4 qs[RECOMPUTE ? MAX_T : 1][D_HEAD / 4][NH];                  // 10 KB (recompute only)
   __shared__ __align__(16) float ps[NH][MAX_T][48];                             // columns >= Tk are zero in the P.V loop
+  // recompute instantiation: the CTA's V tile [Tk][NC] fp32 (dynamic shared memory, ATT_V_SMEM bytes), fetched with
+  // cp.async right after the dependency wait so that it travels under the LayerNorm / score / softmax phases
+  extern __shared__ __align__(16) float vsm[];
   PROF_DECL();
   PROF_BEGIN(4);
   pdl_launch_dependents();
@@ -539,6 +560,14 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
   for (int i = tid; i < NH * MAX_T * 8; i += NT) {
     const int j = Tk + (i & 7);
     if (j < 48) (&ps[0][0][0])[(i >> 3) * 48 + j] = 0.f;
+  }
+  if constexpr (RECOMPUTE) {
+    const float* vrow0 = a.v + (size_t)b * Tk * a.ldv + h0 * D_HEAD;
+    for (int i = tid; i < Tk * (NC / 4); i += NT) {
+      const int j = i / (NC / 4), c4 = i - j * (NC / 4);
+      cp_async16(vsm + j * NC + c4 * 4, vrow0 + (size_t)j * a.ldv + c4 * 4);
+    }
+    cp_async_commit();
   }
 
   if constexpr (RECOMPUTE) {
@@ -623,6 +652,37 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
       const int r = i / Tk, j = i - r * Tk, h = r / T, t = r - h * T;
       ps[h][t][j] = Pg[i];
     }
+  }
+  if constexpr (RECOMPUTE) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (threadIdx.x == 0) PROF_MARK(4);
+    if (tid < NC) {
+      const int h = tid / D_HEAD;
+      float acc[MAX_T];
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t) acc[t] = 0.f;
+      for (int j0 = 0; j0 < Tk; j0 += 4) {
+        float vb4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vb4[k] = (j0 + k < Tk) ? vsm[(j0 + k) * NC + tid] : 0.f;
+#pragma unroll
+        for (int t = 0; t < MAX_T; ++t) {
+          if (t < T) {
+            const float4 p0 = *reinterpret_cast<const float4*>(&ps[h][t][j0]);
+            float s0 = fmaf(p0.x, vb4[0], acc[t]), s1 = p0.y * vb4[1];
+            s0 = fmaf(p0.z, vb4[2], s0);
+            s1 = fmaf(p0.w, vb4[3], s1);
+            acc[t] = s0 + s1;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t)
+        if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + h0 * D_HEAD + tid] = __float2bfloat16(acc[t]);
+    }
+    PROF_END();
+    return;
   }
   // first batch of this thread's V column travels while the barrier is reached
   float vb[8];
