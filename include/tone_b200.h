@@ -87,6 +87,7 @@ typedef struct tone_config {
 
 #define TONE_FLAG_NO_PDL 1         /* launch the kernels of a step without programmatic dependent launch     */
 #define TONE_FLAG_NO_FUSED_VATT 2  /* score-sharing layers: V projection and P.V as two kernels              */
+#define TONE_FLAG_NO_DW_PIPE 4     /* depthwise conv: always the one-CTA-per-(stream, channel half) kernel   */
 
 /* Shapes a caller needs to size its buffers (tone/onnx_wrapper.py:30-34,
  * configs/streaming_acoustic/config.pbtxt:5-33). */

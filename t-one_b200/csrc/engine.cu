@@ -230,6 +230,7 @@ struct tone_engine {
   // but at 1024 streams per GPU 80 row tiles cannot fill 148 SMs (profiles/r02_fused_ff.md).
   int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
+  int dw_pipe_min_batch = 128;   // streams per lane from which the depthwise conv runs as the pipelined persistent kernel (0 = never)
   int num_sms = 148;
 };
 
@@ -374,6 +375,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->num_sms = prop.multiProcessorCount;
   e->pdl = !(cfg->flags & TONE_FLAG_NO_PDL);
   e->fuse_vatt = !(cfg->flags & TONE_FLAG_NO_FUSED_VATT);
+  if (cfg->flags & TONE_FLAG_NO_DW_PIPE) e->dw_pipe_min_batch = 0;
   e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
   e->split_k = cfg->split_k;
   if (cfg->fused_ff) e->ff_fused = cfg->fused_ff - 1;
@@ -544,6 +546,10 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_V_SMEM));
+  CK(cudaFuncSetAttribute(dwconv_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
+  CK(cudaFuncSetAttribute(dwconv_pipe_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
+  CK(cudaFuncSetAttribute(dwconv_pipe_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
+  CK(cudaFuncSetAttribute(dwconv_pipe_kernel<MAX_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
   CK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the engine streams are non-blocking
   return TONE_OK;
 }
@@ -1401,7 +1407,13 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.e = ln.ebuf;
       d.T = Tl;
       const int dw_half = (Tl + 1) / 2;   // output frames per thread
-      if (dw_half <= 3) KLAUNCH(launch_kernel(dwconv_kernel<3>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
+      if (e->dw_pipe_min_batch > 0 && B >= e->dw_pipe_min_batch) {
+        const dim3 grid(std::min(B, 2 * e->num_sms));
+        if (Tl <= 5) KLAUNCH(launch_kernel(dwconv_pipe_kernel<5>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
+        else if (Tl <= 7) KLAUNCH(launch_kernel(dwconv_pipe_kernel<7>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
+        else if (Tl <= 10) KLAUNCH(launch_kernel(dwconv_pipe_kernel<10>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
+        else KLAUNCH(launch_kernel(dwconv_pipe_kernel<MAX_T>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
+      } else if (dw_half <= 3) KLAUNCH(launch_kernel(dwconv_kernel<3>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
       else if (dw_half <= 5) KLAUNCH(launch_kernel(dwconv_kernel<5>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
       else KLAUNCH(launch_kernel(dwconv_kernel<DW_TH>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
     }

@@ -826,6 +826,84 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
   PROF_END();
 }
 
+// Large-batch form: persistent CTAs (two per SM) walk whole streams.  A stream's [30 cached | T new] x 384 tile is two
+// contiguous blocks in global memory (the layer's cache block of the slot, the stream's rows of g), so one thread brings
+// it in with two bulk async copies into a 3-stage ring (the one-CTA-per-(stream, channel half) kernel above has too few
+// bytes in flight per SM to reach the memory system's rate once the batch is in the thousands of rows); thread =
+// channel, all T output frames, taps in registers; the new cache (rows [T, T + 30) of the tile) leaves as one bulk
+// store straight from the tile.
+constexpr int DWP_THREADS = D_MODEL;
+constexpr int DWP_STAGES = 3;
+constexpr int DWP_STAGE_BYTES = (CONV_S + MAX_T) * D_MODEL * 2;      // 33,024
+constexpr int DWP_SMEM = DWP_STAGES * DWP_STAGE_BYTES;
+
+template <int TM>     // TM >= T: compile-time bound of the output frames per stream
+__global__ void __launch_bounds__(DWP_THREADS, 2) dwconv_pipe_kernel(const DwArgs a, int B) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ uint64_t full[DWP_STAGES];
+  PROF_DECL();
+  PROF_BEGIN(5);
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, T = a.T;
+  if (tid == 0) {
+    for (int s = 0; s < DWP_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  float w[CONV_S + 1];
+#pragma unroll
+  for (int j = 0; j <= CONV_S; ++j) w[j] = __ldg(a.w + j * D_MODEL + tid);
+  const float bb = __ldg(a.bias + tid);
+  __syncthreads();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
+  constexpr uint32_t CACHE_BYTES = CONV_S * D_MODEL * 2;
+  const uint32_t g_bytes = (uint32_t)T * D_MODEL * 2;
+  const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int k) {
+    const int b = blockIdx.x + k * gridDim.x, s = k % DWP_STAGES;
+    unsigned char* tile = dsm + s * DWP_STAGE_BYTES;
+    mbar_expect_tx(&full[s], CACHE_BYTES + g_bytes);
+    bulk_load_1d(tile, a.cache + (size_t)a.slots[b] * a.cache_slot_stride, CACHE_BYTES, &full[s]);
+    bulk_load_1d(tile + CACHE_BYTES, a.g + (size_t)b * T * D_MODEL, g_bytes, &full[s]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < DWP_STAGES - 1 && k < nmine; ++k) issue(k);
+  for (int k = 0; k < nmine; ++k) {
+    const int b = blockIdx.x + k * gridDim.x, s = k % DWP_STAGES;
+    if (tid == 0 && k + DWP_STAGES - 1 < nmine) {
+      bulk_wait_read0();            // the cache store of the previous stream has left the stage being refilled
+      issue(k + DWP_STAGES - 1);
+    }
+    mbar_wait(&full[s], (k / DWP_STAGES) & 1);
+    const bf16* tile = reinterpret_cast<const bf16*>(dsm + s * DWP_STAGE_BYTES) + tid;
+    float acc[TM];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) acc[t] = bb;
+#pragma unroll
+    for (int i = 0; i < CONV_S + TM; ++i) {             // tile rows; y[t] = b' + sum_j w'[j] x[t + j]
+      if (i < CONV_S + T) {
+        const float x = __bfloat162float(tile[i * D_MODEL]);
+#pragma unroll
+        for (int t = 0; t < TM; ++t) {
+          const int j = i - t;                               // compile-time after unrolling
+          if (j >= 0 && j <= CONV_S) acc[t] = fmaf(w[j], x, acc[t]);
+        }
+      }
+    }
+    bf16* eo = a.e + (size_t)b * T * D_MODEL + tid;
+#pragma unroll
+    for (int t = 0; t < TM; ++t)
+      if (t < T) eo[t * D_MODEL] = __float2bfloat16(silu_f(acc[t]));
+    __syncthreads();                                      // every thread is done reading the tile
+    if (tid == 0) {                                       // new cache = last 30 rows of [cache | g]
+      bulk_store_1d(a.cache + (size_t)a.slots[b] * a.cache_slot_stride, dsm + s * DWP_STAGE_BYTES + g_bytes, CACHE_BYTES);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait0();
+  PROF_END();
+}
+
 // ------------------------------------------------------------------------------------------------ temporal reduction
 // m[4c+k, t2] = b[4c+k] + sum_j W[4c+k][j] * v[c][2 t2 + j],  v = [red | r^T]  (conformer_blocks.py:874-911).
 struct RedArgs {

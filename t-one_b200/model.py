@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("TONE_B200_LIB") or os.path.join(_HERE, "libtone_b200.
 TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1, -2, -3, -4, -5
 PCM_I32, PCM_I16 = 0, 1
 OUT_LOGPROBS, OUT_TOKENS, OUT_SIL, OUT_PHRASES = 1, 2, 4, 8
-FLAG_NO_PDL, FLAG_NO_FUSED_VATT = 1, 2
+FLAG_NO_PDL, FLAG_NO_FUSED_VATT, FLAG_NO_DW_PIPE = 1, 2, 4
 
 # every symbol include/tone_b200.h declares
 SYMBOLS = (
