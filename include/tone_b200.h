@@ -83,11 +83,20 @@ typedef struct tone_config {
   int32_t fused_ff;          /* feed-forward module as one kernel per row tile (experimental, opt-in):       */
                              /* 1 = off (default), 2 = one CTA per 128 rows, 3 = CTA pairs                   */
   int32_t fused_ff_min_rows; /* rows per lane from which the fused feed-forward is used (default 2048)       */
+  int32_t att_block_min_rows; /* rows per lane from which a score-sharing attention layer runs as ONE kernel  */
+                             /* per tile of whole streams: V projection + P.V + out projection + residual     */
+                             /* (default 4096; -1 = never)                                                    */
+  int32_t lazy_norm_min_rows; /* rows per lane from which feed-forward 1 adds straight into the residual      */
+                             /* stream and norm_self_att becomes a row scale inside the projection GEMMs      */
+                             /* (default 4096; -1 = never)                                                    */
+  int32_t dw_pipe_min_batch; /* streams per lane from which the depthwise conv runs as the pipelined          */
+                             /* persistent kernel (default 128; -1 = never)                                   */
+  int32_t att_pipe_min_batch; /* streams per lane from which the recompute attention layers (0, 7, 14, 15) run */
+                             /* as the pipelined persistent kernel (default 256; -1 = never)                  */
 } tone_config;
 
 #define TONE_FLAG_NO_PDL 1         /* launch the kernels of a step without programmatic dependent launch     */
 #define TONE_FLAG_NO_FUSED_VATT 2  /* score-sharing layers: V projection and P.V as two kernels              */
-#define TONE_FLAG_NO_DW_PIPE 4     /* depthwise conv: always the one-CTA-per-(stream, channel half) kernel   */
 
 /* Shapes a caller needs to size its buffers (tone/onnx_wrapper.py:30-34,
  * configs/streaming_acoustic/config.pbtxt:5-33). */

@@ -31,6 +31,7 @@
 #include "kernels.cuh"
 #include "ctc_phrase.cuh"
 #include "ff_fused.cuh"
+#include "att_fused.cuh"
 #include "state_io.cuh"
 
 using namespace tone;
@@ -106,6 +107,11 @@ struct LayerW {
   float *qln_w, *qln_b, *kln_w, *kln_b;
   float *dw_w, *dw_b;
   CUtensorMap wv48;     // score-sharing layers: Wv with a 48-row box (one head per N tile of the fused V + P.V kernel)
+  // Large-batch path (rows per lane >= BIG_M): the attention input norm is applied as a row scale inside the projection
+  // GEMMs (A = bf16 residual rows from the feed-forward down projection's epilogue), so the norm_self_att gain is folded
+  // into the input columns of these copies (layers 0..13)
+  WeightMat qkv_f;
+  CUtensorMap wv48_f;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -230,6 +236,12 @@ struct tone_engine {
   // but at 1024 streams per GPU 80 row tiles cannot fill 148 SMs (profiles/r02_fused_ff.md).
   int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
+  // score-sharing attention layers as ONE kernel per tile of whole streams (att_fused.cuh) from this many rows per lane (0 = never)
+  int att_block_min_rows = 4096;
+  // feed-forward 1 adds straight into the residual stream and norm_self_att becomes a row scale inside the projection
+  // GEMMs from this many rows per lane (0 = never)
+  int lazy_norm_min_rows = 4096;
+  int att_pipe_min_batch = 256;  // streams per lane from which the recompute attention layers run as the pipelined persistent kernel
   int dw_pipe_min_batch = 128;   // streams per lane from which the depthwise conv runs as the pipelined persistent kernel (0 = never)
   int num_sms = 148;
 };
@@ -318,6 +330,12 @@ static std::vector<float> interleave_rows(const std::vector<float>& a, const std
     }
   return o;
 }
+// W[n][k] * g[k]: a norm gain on the GEMM's input folded into the weight columns
+static std::vector<float> fold_cols(std::vector<float> w, const std::vector<float>& g, int N, int K) {
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) w[(size_t)n * K + k] *= g[k];
+  return w;
+}
 static std::vector<float> concat(std::initializer_list<const std::vector<float>*> parts) {
   std::vector<float> o;
   for (auto p : parts) o.insert(o.end(), p->begin(), p->end());
@@ -343,7 +361,9 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   if (cfg->max_slots < 1 || cfg->max_batch < 1 || cfg->max_batch > cfg->max_slots)
     return fail(TONE_EINVAL, "need 1 <= max_batch <= max_slots");
   if (cfg->lanes < 0 || cfg->lanes > 4 || cfg->persist_mode < 0 || cfg->persist_mode > 3 || cfg->split_k < 0 ||
-      cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0 || cfg->fused_ff < 0 || cfg->fused_ff > 3 || cfg->fused_ff_min_rows < 0)
+      cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0 || cfg->fused_ff < 0 || cfg->fused_ff > 3 || cfg->fused_ff_min_rows < 0 ||
+      cfg->att_block_min_rows < -1 || cfg->lazy_norm_min_rows < -1 || cfg->dw_pipe_min_batch < -1 ||
+      cfg->att_pipe_min_batch < -1)
     return fail(TONE_EINVAL, "tuning field out of range (lanes 0..4, persist_mode 0..3, split_k 0..%d)", (int)MAX_SPLITS);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -375,7 +395,10 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->num_sms = prop.multiProcessorCount;
   e->pdl = !(cfg->flags & TONE_FLAG_NO_PDL);
   e->fuse_vatt = !(cfg->flags & TONE_FLAG_NO_FUSED_VATT);
-  if (cfg->flags & TONE_FLAG_NO_DW_PIPE) e->dw_pipe_min_batch = 0;
+  if (cfg->att_block_min_rows) e->att_block_min_rows = std::max(0, cfg->att_block_min_rows);      // -1 = never
+  if (cfg->lazy_norm_min_rows) e->lazy_norm_min_rows = std::max(0, cfg->lazy_norm_min_rows);
+  if (cfg->dw_pipe_min_batch) e->dw_pipe_min_batch = std::max(0, cfg->dw_pipe_min_batch);
+  if (cfg->att_pipe_min_batch) e->att_pipe_min_batch = std::max(0, cfg->att_pipe_min_batch);
   e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
   e->split_k = cfg->split_k;
   if (cfg->fused_ff) e->ff_fused = cfg->fused_ff - 1;
@@ -400,7 +423,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
     e->encode = (PFN_encodeTiled)fn;
   }
   // weight arena: ~72M params in bf16 + expanded conv matrices + fp32 vectors
-  e->w_cap = (size_t)200 << 20;
+  e->w_cap = (size_t)256 << 20;
   CK(cudaMalloc((void**)&e->w_arena, e->w_cap));
   CK(cudaMemset(e->w_arena, 0, e->w_cap));
 
@@ -542,10 +565,13 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_gemm_tc_persist<G_PARTIAL, 1, false>()));
   CK((configure_ff_fused<false>()));
   CK((configure_ff_fused<true>()));
+  CK(configure_att_fused());
   e->persist_ctas = e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_V_SMEM));
+  CK(cudaFuncSetAttribute(attention_pipe_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+  CK(cudaFuncSetAttribute(attention_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CK(cudaFuncSetAttribute(dwconv_pipe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
   CK(cudaFuncSetAttribute(dwconv_pipe_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
   CK(cudaFuncSetAttribute(dwconv_pipe_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWP_SMEM));
@@ -847,6 +873,10 @@ static int finalize_layer(tone_engine* e, int l) {
       if ((rc = upload_mat(e, concat({&wq->data, &wk->data, &wv->data}), 3 * D_MODEL, D_MODEL, BN_STORE, &L.qkv)))
         return rc;
       if ((rc = upload_f32(e, concat({&bq->data, &bk->data, &bv->data}), &L.qkv_b))) return rc;
+      NEEDW(gat, Lp + "norm_self_att.weight");
+      if ((rc = upload_mat(e, fold_cols(concat({&wq->data, &wk->data, &wv->data}), gat->data, 3 * D_MODEL, D_MODEL),
+                           3 * D_MODEL, D_MODEL, BN_STORE, &L.qkv_f)))
+        return rc;
     } else {       // q on the T new rows, k | v on the S+T [cache | new] rows
       if ((rc = upload_mat(e, wq->data, D_MODEL, D_MODEL, BN_STORE, &L.q))) return rc;
       if ((rc = upload_f32(e, bq->data, &L.q_b))) return rc;
@@ -865,6 +895,9 @@ static int finalize_layer(tone_engine* e, int l) {
     if ((rc = upload_mat(e, wv->data, D_MODEL, D_MODEL, BN_STORE, &L.qkv))) return rc;
     if ((rc = upload_f32(e, bv->data, &L.qkv_b))) return rc;
     if ((rc = make_map_2d(e, &L.wv48, L.qkv.ptr, D_MODEL, D_MODEL, D_HEAD, true))) return rc;
+    NEEDW(gat, Lp + "norm_self_att.weight");
+    if ((rc = upload_mat(e, fold_cols(wv->data, gat->data, D_MODEL, D_MODEL), D_MODEL, D_MODEL, BN_STORE, &L.qkv_f))) return rc;
+    if ((rc = make_map_2d(e, &L.wv48_f, L.qkv_f.ptr, D_MODEL, D_MODEL, D_HEAD, true))) return rc;
   }
   // conv module: pw1 rows [0,384) = a, [384,768) = b (GLU = a * sigmoid(b), conformer_blocks.py:422)
   const std::string Cp = Lp + "conv.";
@@ -1100,8 +1133,14 @@ static int run_norm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, floa
 
 // Feed-forward: h = silu(n W1^T + b1) * (n Wv^T + bv); the down projection runs split-K and leaves its partial
 // sums in ln.part; the NEXT norm kernel adds 0.5 * (sum + b2) to the residual stream (conformer_blocks.py:814,834).
+static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const bf16* A,
+                              const CUtensorMap& mapA, const WeightMat& w, const float* bias, float* r, int* ss_tiles,
+                              int K, float scale);
+// resid_r != nullptr (large batches, no split-K): the down projection adds 0.5 * (acc + b2) to the residual stream in
+// its own epilogue and emits bf16(r) + the row sums of squares (*resid_ss_tiles tiles), so that the NEXT GEMM applies
+// the following RMSNorm as a row scale - no partial sums through HBM and no norm kernel.
 static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const WeightMat& up, const float* up_b, const WeightMat& down,
-                  const float* down_b, PartIn* out, int ss_tiles = 0) {
+                  const float* down_b, PartIn* out, int ss_tiles = 0, float* resid_r = nullptr, int* resid_ss_tiles = nullptr) {
   const int mt = (M + 127) / 128;
   // ss_tiles > 0: the input is the un-normalised residual in bf16 (ln.rb) with its row sums of squares in ln.ss
   GemmArgs a = dense_args(M, D_MODEL, ss_tiles ? ln.rb : ln.n, ln.h, D_FF, up_b, 1.f);
@@ -1111,6 +1150,10 @@ static int run_ff(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M,
     a.ss_tiles = ss_tiles;
   }
   RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ss_tiles ? ln.m_rb : ln.m_n, up, a, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+  if (resid_r) {
+    *out = PartIn();
+    return run_resid_rowscale(e, ln, st, M, ln.h, ln.m_h, down, down_b, resid_r, resid_ss_tiles, D_FF, 0.5f);
+  }
   int splits = 1;
   while (splits < e->max_splits && mt * (D_MODEL / BN_PART) * splits * 2 <= e->num_sms) splits *= 2;  // fill the SMs once
   if (e->split_k) splits = e->split_k;
@@ -1166,9 +1209,10 @@ static int run_ff_fused(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, 
 // r += A W^T + b through the tensor cores; also emits bf16(r) and the per-tile row sums of squares that let the next
 // GEMM apply the following RMSNorm as a row scale.  Returns the number of ss tiles through *ss_tiles.
 static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, const bf16* A,
-                              const CUtensorMap& mapA, const WeightMat& w, const float* bias, float* r, int* ss_tiles) {
+                              const CUtensorMap& mapA, const WeightMat& w, const float* bias, float* r, int* ss_tiles,
+                              int K, float scale) {
   const int mt = (M + 127) / 128;
-  GemmArgs a = dense_args(M, D_MODEL, A, r, D_MODEL, bias, 1.f);
+  GemmArgs a = dense_args(M, K, A, r, D_MODEL, bias, scale);
   if (e->cfg.gemm_impl == 0) {
     a.rb_out = ln.rb;
     a.ss_out = ln.ss;
@@ -1280,11 +1324,18 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     const int mt = (M + 127) / 128;
     PartIn ff;
     const bool fused_ff = use_ff_fused(e, M);
+    // large batches, layers 0..13: feed-forward 1 goes straight into the residual stream and norm_self_att becomes a row
+    // scale inside the q / k / v projections (layers 14 / 15 need the normalised rows themselves for their caches)
+    const bool lazy_att = !fused_ff && e->lazy_norm_min_rows > 0 && e->cfg.gemm_impl == 0 && M >= std::max(e->lazy_norm_min_rows, BIG_M) &&
+                          l < 14 && (RECOMPUTE[l] || e->fuse_vatt);
+    int att_ss_tiles = 0;
     if (fused_ff) {   // feed-forward 1 + residual + norm_self_att (+ cache-row scatter of layers 14 / 15) in one kernel
       if (l < 14) RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n));
       else
         RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n,
                         l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
+    } else if (lazy_att) {
+      RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff, 0, r, &att_ss_tiles));
     } else {
       RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff));
     }
@@ -1298,14 +1349,19 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     at.len_in = ln.len_in;
     at.T = Tl;
     at.recompute = RECOMPUTE[l] ? 1 : 0;
-    bool fused_att = false;
+    bool fused_att = false, att_block = false;
     if (l < 14) {
-      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
+      if (!fused_ff && !lazy_att) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
-        GemmArgs a = dense_args(M, D_MODEL, ln.n, ln.qkv, 3 * D_MODEL, L.qkv_b, 1.f);
-        if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / 128, M, 3 * D_MODEL, nullptr, 1, true)));
+        GemmArgs a = dense_args(M, D_MODEL, lazy_att ? ln.rb : ln.n, ln.qkv, 3 * D_MODEL, L.qkv_b, 1.f);
+        if (lazy_att) {
+          a.ss = ln.ss;
+          a.ss_ld = 12;
+          a.ss_tiles = att_ss_tiles;
+          RC((gemm<G_STORE_F32, 128>(e, st, ln.m_rb, L.qkv_f, a, mt, 3 * D_MODEL / 128, M, 3 * D_MODEL, nullptr, 1, true)));
+        } else if (M >= BIG_M) RC((gemm<G_STORE_F32, 128>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / 128, M, 3 * D_MODEL, nullptr, 1, true)));
         else RC((gemm<G_STORE_F32, BN_STORE>(e, st, ln.m_n, L.qkv, a, mt, 3 * D_MODEL / BN_STORE, M, 3 * D_MODEL)));
         at.q = ln.qkv;
         at.k = ln.qkv + D_MODEL;
@@ -1315,6 +1371,31 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
         at.q_ln_b = L.qln_b;
         at.k_ln_w = L.kln_w;
         at.k_ln_b = L.kln_b;
+      } else if (e->cfg.gemm_impl == 0 && e->fuse_vatt && e->att_block_min_rows > 0 && M >= e->att_block_min_rows) {
+        // score-sharing layer, large batch: V projection + P.V + out projection + residual in ONE kernel per tile of
+        // whole streams
+        AttFArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.B = B;
+        fa.R = Tl;
+        fa.G = 128 / Tl;
+        fa.P = ln.P;
+        fa.bv = L.qkv_b;
+        fa.bo = L.wo_b;
+        if (lazy_att) {
+          fa.ss = ln.ss;
+          fa.ss_tiles = att_ss_tiles;
+        }
+        fa.ss_ld = 12;
+        fa.r = r;
+        fa.rb_out = ln.rb;
+        fa.ss_out = ln.ss;
+        cudaError_t err = launch_att_fused(st, lazy_att ? ln.m_rb : ln.m_n, lazy_att ? L.qkv_f.map128 : L.qkv.map128,
+                                           L.wo.map128, fa, e->pdl);
+        e->launches++;
+        if (err != cudaSuccess) return fail(TONE_ECUDA, "fused attention block launch: %s", cudaGetErrorString(err));
+        fused_att = true;
+        att_block = true;
       } else if (e->cfg.gemm_impl == 0 && e->fuse_vatt) {
         // score-sharing layer: ctx = P (n Wv^T + bv) per head in ONE kernel; tiles = whole streams x one head
         GemmArgs a;
@@ -1327,10 +1408,16 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
         a.ldo = D_MODEL;
         a.bias = L.qkv_b;
         a.P = ln.P;
-        a.A = ln.n;
+        a.A = lazy_att ? ln.rb : ln.n;
         a.lda = D_MODEL;
-        cudaError_t err = launch_gemm_tc<G_VATT, D_HEAD>(st, ln.m_n, ln.m_n, L.wv48, a, (B + a.G - 1) / a.G, N_HEADS, e->pdl,
-                                                         e->num_sms);
+        if (lazy_att) {
+          a.ss = ln.ss;
+          a.ss_ld = 12;
+          a.ss_tiles = att_ss_tiles;
+        }
+        const CUtensorMap& mA = lazy_att ? ln.m_rb : ln.m_n;
+        cudaError_t err = launch_gemm_tc<G_VATT, D_HEAD>(st, mA, mA, lazy_att ? L.wv48_f : L.wv48, a, (B + a.G - 1) / a.G,
+                                                         N_HEADS, e->pdl, e->num_sms);
         e->launches++;
         if (err != cudaSuccess) return fail(TONE_ECUDA, "fused V + attention launch: %s", cudaGetErrorString(err));
         fused_att = true;
@@ -1383,10 +1470,17 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       at.mask_mode = (l == 14) ? 2 : 1;
     }
     if (fused_att) {
+    } else if (RECOMPUTE[l] && e->att_pipe_min_batch > 0 && B >= e->att_pipe_min_batch) {
+      const size_t smem = (size_t)ATP_FIXED_SMEM + (size_t)(2 * at.Tk + at.T) * (D_MODEL * 4 + ATP_PAD);
+      if (at.S > 0)
+        KLAUNCH(launch_kernel(attention_pipe_kernel<512>, dim3(std::min(B, e->num_sms)), dim3(512), smem, st, e->pdl, at, B));
+      else
+        KLAUNCH(launch_kernel(attention_pipe_kernel<256>, dim3(std::min(B, 2 * e->num_sms)), dim3(256), smem, st, e->pdl, at, B));
     } else if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), ATT_V_SMEM, st, e->pdl, at));
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
-    RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles));
+    if (att_block) ss_tiles = 1;      // the fused kernel owns whole rows: one sum of squares per row
+    else RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles, D_MODEL, 1.f));
     // ---- convolution module: norm_conv is applied as a row scale inside the pointwise-conv GEMM (A = bf16(r))
     {
       {
@@ -1417,7 +1511,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       else if (dw_half <= 5) KLAUNCH(launch_kernel(dwconv_kernel<5>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
       else KLAUNCH(launch_kernel(dwconv_kernel<DW_TH>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
     }
-    RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles));
+    RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles, D_MODEL, 1.f));
     // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer
     if (fused_ff) {   // feed-forward 2 + residual + norm_out + the next layer's first norm in one kernel
       const float* g1 = l == 14 ? nullptr : L.n_out;

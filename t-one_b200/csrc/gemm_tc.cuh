@@ -236,6 +236,17 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         for (int j = 0; j < VATT_MAX_T; ++j) pr[k][j] = j < R ? __ldg(pp + j) : 0.f;
       }
     }
+    // row-scale RMSNorm folded around the V projection (A = bf16 residual rows, gain folded into the weights)
+    float rsv = 1.f;
+    if (a.ss) {
+      const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
+      if (rme.valid) {
+        const float* sp = a.ss + rme.out_row * a.ss_ld;
+        float tsum = 0.f;
+        for (int k = 0; k < a.ss_tiles; ++k) tsum += sp[k];
+        rsv = 1.0f / (sqrtf(tsum) * 0.05103103630798288f + 1e-8f);
+      }
+    }
     mbar_wait(tmem_full, 0);
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
@@ -251,10 +262,10 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
 #pragma unroll
       for (int c = 0; c < 24; c += 4) {
         float4 o;
-        o.x = __uint_as_float(c < 16 ? r0[c] : r1[c - 16]) + s_c0[24 * hf + c];
-        o.y = __uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]) + s_c0[24 * hf + c + 1];
-        o.z = __uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]) + s_c0[24 * hf + c + 2];
-        o.w = __uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]) + s_c0[24 * hf + c + 3];
+        o.x = fmaf(__uint_as_float(c < 16 ? r0[c] : r1[c - 16]), rsv, s_c0[24 * hf + c]);
+        o.y = fmaf(__uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]), rsv, s_c0[24 * hf + c + 1]);
+        o.z = fmaf(__uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]), rsv, s_c0[24 * hf + c + 2]);
+        o.w = fmaf(__uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]), rsv, s_c0[24 * hf + c + 3]);
         *reinterpret_cast<float4*>(vr + c) = o;
       }
     }
@@ -300,7 +311,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
     }
     // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
     float rs = 1.f;
-    if constexpr (gated) {
+    if constexpr (gated || KIND == G_STORE_F32) {
       if (a.ss) {
         const RowInfo rme = row_info<KIND>(a, q * 32 + lane);
         if (rme.valid) {
@@ -328,10 +339,17 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
         {
           const float4 bb = lds128(c0a + (cbase + c) * 4);
-          o.x += bb.x;
-          o.y += bb.y;
-          o.z += bb.z;
-          o.w += bb.w;
+          if constexpr (KIND == G_STORE_F32) {   // optional row-scale RMSNorm of the A rows (rs = 1 without it)
+            o.x = fmaf(o.x, rs, bb.x);
+            o.y = fmaf(o.y, rs, bb.y);
+            o.z = fmaf(o.z, rs, bb.z);
+            o.w = fmaf(o.w, rs, bb.w);
+          } else {
+            o.x += bb.x;
+            o.y += bb.y;
+            o.z += bb.z;
+            o.w += bb.w;
+          }
         }
         if constexpr (KIND == G_RESID) {
           o.x *= a.scale;
@@ -553,6 +571,16 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
         for (int j = 0; j < VATT_MAX_T; ++j) pr[k][j] = j < R ? __ldg(pp + j) : 0.f;
       }
     }
+    float rsv = 1.f;
+    if (a.ss) {
+      const RowInfo rme = row_info_p<KIND, PERSIST>(a, tx, q * 32 + lane);
+      if (rme.valid) {
+        const float* sp = a.ss + rme.out_row * a.ss_ld;
+        float tsum = 0.f;
+        for (int k = 0; k < a.ss_tiles; ++k) tsum += sp[k];
+        rsv = 1.0f / (sqrtf(tsum) * 0.05103103630798288f + 1e-8f);
+      }
+    }
     mbar_wait(tmem_full, par);
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
@@ -568,10 +596,10 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
 #pragma unroll
       for (int c = 0; c < 24; c += 4) {
         float4 o;
-        o.x = __uint_as_float(c < 16 ? r0[c] : r1[c - 16]) + s_c0[24 * hf + c];
-        o.y = __uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]) + s_c0[24 * hf + c + 1];
-        o.z = __uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]) + s_c0[24 * hf + c + 2];
-        o.w = __uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]) + s_c0[24 * hf + c + 3];
+        o.x = fmaf(__uint_as_float(c < 16 ? r0[c] : r1[c - 16]), rsv, s_c0[24 * hf + c]);
+        o.y = fmaf(__uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]), rsv, s_c0[24 * hf + c + 1]);
+        o.z = fmaf(__uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]), rsv, s_c0[24 * hf + c + 2]);
+        o.w = fmaf(__uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]), rsv, s_c0[24 * hf + c + 3]);
         *reinterpret_cast<float4*>(vr + c) = o;
       }
     }
@@ -617,7 +645,7 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
     }
     // consumer side of the row-scale RMSNorm: 1 / (rms + eps) of this thread's row, from the producer's partial sums
     float rs = 1.f;
-    if constexpr (gated) {
+    if constexpr (gated || KIND == G_STORE_F32) {
       if (rs_pre) {
         rs = *rs_pre;
       } else if (a.ss) {
@@ -647,10 +675,17 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
         float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
         {
           const float4 bb = lds128(c0a + (cbase + c) * 4);
-          o.x += bb.x;
-          o.y += bb.y;
-          o.z += bb.z;
-          o.w += bb.w;
+          if constexpr (KIND == G_STORE_F32) {   // optional row-scale RMSNorm of the A rows (rs = 1 without it)
+            o.x = fmaf(o.x, rs, bb.x);
+            o.y = fmaf(o.y, rs, bb.y);
+            o.z = fmaf(o.z, rs, bb.z);
+            o.w = fmaf(o.w, rs, bb.w);
+          } else {
+            o.x += bb.x;
+            o.y += bb.y;
+            o.z += bb.z;
+            o.w += bb.w;
+          }
         }
         if constexpr (KIND == G_RESID) {
           o.x *= a.scale;
@@ -1172,7 +1207,7 @@ __global__ void __launch_bounds__(PersistCfg<KIND, NSUB, PAIR>::THREADS, 1) gemm
       first = false;
       // row scale of the folded RMSNorm: one value per row, shared by the sub-tiles
       float rs = 1.f;
-      if constexpr (KIND == G_SWIGLU || KIND == G_GLU) {
+      if constexpr (KIND == G_SWIGLU || KIND == G_GLU || KIND == G_STORE_F32) {
         if (a.ss) {
           const RowInfo rme = row_info_p<KIND, true>(a, tx, q * 32 + lane);
           if (rme.valid) {

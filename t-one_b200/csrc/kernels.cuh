@@ -727,6 +727,274 @@ __global__ void __launch_bounds__(RECOMPUTE ? ATT_THREADS_REC : ATT_THREADS) att
   PROF_END();
 }
 
+// Large-batch form of the recompute layers (0, 7, 14, 15): persistent CTAs walk whole streams (512 threads, one CTA per
+// SM for the cached-context layers 14 / 15; 256 threads, two CTAs per SM for layers 0 / 7).  A stream's q / k / v rows
+// are contiguous blocks of the projection outputs, so one warp brings them into shared memory with bulk async copies,
+// one per row (rows padded by 16 B: the per-(key, head) LayerNorm reads then spread over the banks).  The k + q rows
+// and the v rows have their own buffers and barriers: k / q of stream i + 1 are requested as soon as the LayerNorm phase
+// of stream i has put them in registers, v of stream i + 1 when the P.V phase of stream i is over - both travel under
+// the arithmetic of the phases that do not need them.  LayerNorm gains and the RoPE table are staged in shared memory
+// once per CTA.  The one-CTA-per-(stream, head half) kernel above is a chain of dependent global round trips at two
+// CTAs per SM: 7 waves of ~10 us at 1024 streams.
+constexpr int ATP_PAD = 16;
+constexpr int ATP_QS = MAX_T * (D_HEAD / 4) * N_HEADS * 16;          // 19,968: query rows [t][d / 4][head] float4
+constexpr int ATP_PS = N_HEADS * MAX_T * 48 * 4;                     // 19,968: scores / probabilities
+constexpr int ATP_PAR = (4 * D_HEAD + 2 * (MHSA_S + MAX_T) * 16) * 4;   // q/k LayerNorm gain + bias, RoPE cos | sin: 6,272
+constexpr int ATP_FIXED_SMEM = ATP_QS + ATP_PS + ATP_PAR;
+
+__host__ __device__ inline int atp_kq_bytes(int T, int Tk) { return (Tk + T) * (D_MODEL * 4 + ATP_PAD) + (Tk == T ? T * D_MODEL * 4 : 0); }
+__host__ __device__ inline int atp_v_bytes(int Tk) { return Tk * (D_MODEL * 4 + ATP_PAD); }
+
+// LayerNorm(48) + RoPE of one (row, head) slice held in shared memory; parameters in shared memory as float4
+__device__ __forceinline__ void ln_rope_row_s(const float* src, const float4* w4, const float4* b4, const float4* cs4,
+                                              const float4* sn4, float scale, float* x) {
+#pragma unroll
+  for (int i = 0; i < D_HEAD; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + i);
+    x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w;
+  }
+  float m4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < D_HEAD; i += 4) {
+    m4[0] += x[i];
+    m4[1] += x[i + 1];
+    m4[2] += x[i + 2];
+    m4[3] += x[i + 3];
+  }
+  const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.0f / D_HEAD);
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < D_HEAD; i += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = x[i + k] - mean;
+      v4[k] = fmaf(d, d, v4[k]);
+    }
+  }
+  const float var = (v4[0] + v4[1]) + (v4[2] + v4[3]);
+  const float inv = rsqrtf(var * (1.0f / D_HEAD) + 1e-5f);   // nn.LayerNorm(48), submodules.py:200-201
+#pragma unroll
+  for (int i = 0; i < D_HEAD; i += 4) {
+    const float4 w = w4[i >> 2], bb = b4[i >> 2];
+    x[i] = (x[i] - mean) * inv * w.x + bb.x;
+    x[i + 1] = (x[i + 1] - mean) * inv * w.y + bb.y;
+    x[i + 2] = (x[i + 2] - mean) * inv * w.z + bb.z;
+    x[i + 3] = (x[i + 3] - mean) * inv * w.w + bb.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {                           // RoPE on dims [0,32): pairs (i, i+16)
+    const float4 c = cs4[i >> 2], sn = sn4[i >> 2];
+    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x1 = x[i + k], x2 = x[i + k + 16];
+      x[i + k] = x1 * cc[k] - x2 * ss[k];
+      x[i + k + 16] = x2 * cc[k] + x1 * ss[k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D_HEAD; ++i) x[i] *= scale;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(const AttnArgs a, int B) {
+  extern __shared__ __align__(128) unsigned char asm_[];
+  __shared__ uint64_t kq_full, v_full;
+  PROF_DECL();
+  PROF_BEGIN(4);
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = a.T, Tk = a.Tk, S = a.S;
+  const bool cached = S > 0;
+  constexpr int RS = D_MODEL * 4 + ATP_PAD;                 // padded row of 384 floats
+  float4* qs = reinterpret_cast<float4*>(asm_);                          // [MAX_T][12][8]
+  float* ps = reinterpret_cast<float*>(asm_ + ATP_QS);                   // [8][MAX_T][48]
+  float* par = reinterpret_cast<float*>(asm_ + ATP_QS + ATP_PS);         // q_w | q_b | k_w | k_b | cos | sin
+  const float4* qw4 = reinterpret_cast<const float4*>(par);
+  const float4* qb4 = qw4 + D_HEAD / 4;
+  const float4* kw4 = qb4 + D_HEAD / 4;
+  const float4* kb4 = kw4 + D_HEAD / 4;
+  const float4* cos4 = kb4 + D_HEAD / 4;                                  // [MHSA_S + MAX_T][4]
+  const float4* sin4 = cos4 + (MHSA_S + MAX_T) * 4;
+  unsigned char* kbuf = asm_ + ATP_FIXED_SMEM;                            // k rows [Tk][RS]
+  unsigned char* qbuf = kbuf + Tk * RS;                                   // q rows [T][RS]
+  unsigned char* vbuf = qbuf + T * RS;                                    // v rows [Tk][RS]
+  if (tid == 0) {
+    mbar_init(&kq_full, 1);
+    mbar_init(&v_full, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < N_HEADS * MAX_T * 48; i += NT) ps[i] = 0.f;   // columns >= Tk stay zero for the P.V loop
+  for (int i = tid; i < D_HEAD; i += NT) {
+    par[i] = __ldg(a.q_ln_w + i);
+    par[D_HEAD + i] = __ldg(a.q_ln_b + i);
+    par[2 * D_HEAD + i] = __ldg(a.k_ln_w + i);
+    par[3 * D_HEAD + i] = __ldg(a.k_ln_b + i);
+  }
+  for (int i = tid; i < (MHSA_S + MAX_T) * 16; i += NT) {
+    par[4 * D_HEAD + i] = __ldg(a.rope_cos + i);
+    par[4 * D_HEAD + (MHSA_S + MAX_T) * 16 + i] = __ldg(a.rope_sin + i);
+  }
+  __syncthreads();
+  pdl_wait();
+  if (threadIdx.x == 0) PROF_MARK(2);
+  const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // warp 0: bulk copies of stream number k of this CTA.  Uncached layers: rows of [q | k | v] (ldq = 1152 floats);
+  // cached layers: k | v rows from the K/V projection (ldk = 768 floats), q rows from the Q projection.
+  auto issue_kq = [&](int k) {
+    const int b = blockIdx.x + k * gridDim.x;
+    if (lane == 0) mbar_expect_tx(&kq_full, (uint32_t)((Tk + T) * D_MODEL * 4));
+    __syncwarp();
+    for (int j = lane; j < Tk; j += 32) bulk_load_1d(kbuf + j * RS, a.k + (size_t)(b * Tk + j) * a.ldk, D_MODEL * 4, &kq_full);
+    for (int t = lane; t < T; t += 32) bulk_load_1d(qbuf + t * RS, a.q + (size_t)(b * T + t) * a.ldq, D_MODEL * 4, &kq_full);
+  };
+  auto issue_v = [&](int k) {
+    const int b = blockIdx.x + k * gridDim.x;
+    if (lane == 0) mbar_expect_tx(&v_full, (uint32_t)(Tk * D_MODEL * 4));
+    __syncwarp();
+    for (int j = lane; j < Tk; j += 32) bulk_load_1d(vbuf + j * RS, a.v + (size_t)(b * Tk + j) * a.ldv, D_MODEL * 4, &v_full);
+  };
+  if (warp == 0 && nmine > 0) {
+    issue_kq(0);
+    issue_v(0);
+  }
+  const int nk = Tk * N_HEADS, nq = T * N_HEADS;
+#ifdef TONE_PROF
+  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define ATP_TS(i) if (k == 1) tp[i] = clock64()
+#else
+#define ATP_TS(i)
+#endif
+  for (int k = 0; k < nmine; ++k) {
+    const int b = blockIdx.x + k * gridDim.x;
+    ATP_TS(0);
+    mbar_wait(&kq_full, k & 1);
+    ATP_TS(1);
+    if (k == 1 && threadIdx.x == 0) PROF_MARK(1);
+    // ---- per-head LayerNorm + RoPE: key rows stay in registers, query rows go to shared memory (items beyond the
+    // thread count of the 256-thread form take a second pass)
+    float kx[D_HEAD];
+    int kj = -1, kh = 0;
+    if (tid < nk) {
+      kh = tid / Tk;
+      kj = tid - kh * Tk;
+      ln_rope_row_s(reinterpret_cast<const float*>(kbuf + kj * RS) + kh * D_HEAD, kw4, kb4, cos4 + (kj - S + MHSA_S) * 4,
+                    sin4 + (kj - S + MHSA_S) * 4, 1.0f, kx);
+    }
+    for (int i = tid - nk; i < nq; i += NT) {
+      if (i < 0) continue;
+      const int h = i / T, t = i - h * T;
+      float qx[D_HEAD];
+      ln_rope_row_s(reinterpret_cast<const float*>(qbuf + t * RS) + h * D_HEAD, qw4, qb4, cos4 + (t + MHSA_S) * 4,
+                    sin4 + (t + MHSA_S) * 4, 0.14433756729740643f /* 1/sqrt(48) */, qx);
+#pragma unroll
+      for (int d = 0; d < D_HEAD; d += 4) qs[(t * (D_HEAD / 4) + (d >> 2)) * N_HEADS + h] = make_float4(qx[d], qx[d + 1], qx[d + 2], qx[d + 3]);
+    }
+    __syncthreads();                                         // k / q rows are in registers / qs: their buffers are free
+    ATP_TS(2);
+    if (k == 1 && threadIdx.x == 0) PROF_MARK(3);
+    if (warp == 0 && k + 1 < nmine) issue_kq(k + 1);
+    int off = 0;
+    if (a.mask_mode == 1) off = MHSA_S - a.len_in[b];
+    else if (a.mask_mode == 2) off = (MHSA_S - a.len_in[b]) / 2;
+    if (kj >= 0) {
+      const bool masked = kj < off;                              // cache columns older than the stream
+      for (int t = 0; t < T; ++t) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < D_HEAD; d += 4) {
+          const float4 qv = qs[(t * (D_HEAD / 4) + (d >> 2)) * N_HEADS + kh];
+          s0 = fmaf(qv.x, kx[d], s0);
+          s1 = fmaf(qv.y, kx[d + 1], s1);
+          s2 = fmaf(qv.z, kx[d + 2], s2);
+          s3 = fmaf(qv.w, kx[d + 3], s3);
+        }
+        ps[(kh * MAX_T + t) * 48 + kj] = masked ? -10000.0f : (s0 + s1) + (s2 + s3);   // submodules.py:261
+      }
+    }
+    __syncthreads();
+    ATP_TS(3);
+    // ---- masked softmax: 8 lanes per (head, query) row; P is published for the score-sharing layers
+    {
+      float* Pg = a.P + (size_t)b * N_HEADS * T * Tk;
+      const int g = tid >> 3, l8 = tid & 7;
+      for (int r = g; r < nq; r += NT / 8) {
+        const int h = r / T, t = r - h * T;
+        float* pr = ps + (h * MAX_T + t) * 48;
+        float e[6];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int j = l8 + 8 * q;
+          e[q] = j < Tk ? pr[j] : -INFINITY;
+          mx = fmaxf(mx, e[q]);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          e[q] = (l8 + 8 * q < Tk) ? expf(e[q] - mx) : 0.f;
+          sum += e[q];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        float* pg = Pg + (size_t)(h * T + t) * Tk;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int j = l8 + 8 * q;
+          if (j < Tk) {
+            const float p = (j < off) ? 0.f : e[q] * inv;          // submodules.py:262
+            pr[j] = p;
+            pg[j] = p;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (k == 1 && threadIdx.x == 0) PROF_MARK(4);
+    // ---- ctx = P v: thread = (head, dim), V read from its buffer
+    ATP_TS(4);
+    mbar_wait(&v_full, k & 1);
+    ATP_TS(5);
+    for (int c = tid; c < D_MODEL; c += NT) {
+      const int h = c / D_HEAD;
+      const float* vcol = reinterpret_cast<const float*>(vbuf) + c;
+      float acc[MAX_T];
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t) acc[t] = 0.f;
+      for (int j0 = 0; j0 < Tk; j0 += 4) {
+        float vb4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vb4[q] = (j0 + q < Tk) ? vcol[(j0 + q) * (RS / 4)] : 0.f;
+#pragma unroll
+        for (int t = 0; t < MAX_T; ++t) {
+          if (t < T) {
+            const float4 p0 = *reinterpret_cast<const float4*>(ps + (h * MAX_T + t) * 48 + j0);
+            float s0 = fmaf(p0.x, vb4[0], acc[t]), s1 = p0.y * vb4[1];
+            s0 = fmaf(p0.z, vb4[2], s0);
+            s1 = fmaf(p0.w, vb4[3], s1);
+            acc[t] = s0 + s1;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < MAX_T; ++t)
+        if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + c] = __float2bfloat16(acc[t]);
+    }
+    __syncthreads();                                         // the v buffer and ps are free again
+    ATP_TS(6);
+    if (warp == 0 && k + 1 < nmine) issue_v(k + 1);
+  }
+#ifdef TONE_PROF
+  if (blockIdx.x == 0 && tid == 0 && g_prof)
+    printf("attn pipe T %d Tk %d: wait_kq %lld ln %lld scores %lld softmax %lld wait_v %lld pv %lld\n", T, Tk, tp[1] - tp[0], tp[2] - tp[1],
+           tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], tp[6] - tp[5]);
+#endif
+  PROF_END();
+}
+
 // ------------------------------------------------------------------------------------------------ depthwise conv
 struct DwArgs {
   const bf16* g;        // [B*T][384] GLU output of this layer

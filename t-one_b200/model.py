@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("TONE_B200_LIB") or os.path.join(_HERE, "libtone_b200.
 TONE_OK, TONE_EINVAL, TONE_ENOMEM, TONE_ECUDA, TONE_ESTATE, TONE_ERANGE = 0, -1, -2, -3, -4, -5
 PCM_I32, PCM_I16 = 0, 1
 OUT_LOGPROBS, OUT_TOKENS, OUT_SIL, OUT_PHRASES = 1, 2, 4, 8
-FLAG_NO_PDL, FLAG_NO_FUSED_VATT, FLAG_NO_DW_PIPE = 1, 2, 4
+FLAG_NO_PDL, FLAG_NO_FUSED_VATT = 1, 2
 
 # every symbol include/tone_b200.h declares
 SYMBOLS = (
@@ -43,7 +43,8 @@ class ToneConfig(C.Structure):
                 ("max_batch", C.c_int32), ("gemm_impl", C.c_int32), ("use_graph", C.c_int32),
                 ("lanes", C.c_int32), ("lane_min_batch", C.c_int32), ("persist_min_tiles", C.c_int32),
                 ("persist_mode", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32),
-                ("fused_ff", C.c_int32), ("fused_ff_min_rows", C.c_int32)]
+                ("fused_ff", C.c_int32), ("fused_ff_min_rows", C.c_int32), ("att_block_min_rows", C.c_int32),
+                ("lazy_norm_min_rows", C.c_int32), ("dw_pipe_min_batch", C.c_int32), ("att_pipe_min_batch", C.c_int32)]
 
 
 class ToneInfo(C.Structure):
@@ -182,11 +183,13 @@ class Engine:
     def __init__(self, weights=None, chunk_samples: int = 2400, max_slots: int = 64, max_batch: Optional[int] = None,
                  device: int = 0, gemm_impl: int = 0, use_graph: bool = True, *, lanes: int = 0, lane_min_batch: int = 0,
                  persist_min_tiles: int = 0, persist_mode: int = 0, split_k: int = 0, flags: int = 0,
-                 fused_ff: int = 0, fused_ff_min_rows: int = 0):
+                 fused_ff: int = 0, fused_ff_min_rows: int = 0, att_block_min_rows: int = 0, lazy_norm_min_rows: int = 0,
+                 dw_pipe_min_batch: int = 0, att_pipe_min_batch: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph),
-                         lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags, fused_ff, fused_ff_min_rows)
+                         lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags, fused_ff, fused_ff_min_rows,
+                         att_block_min_rows, lazy_norm_min_rows, dw_pipe_min_batch, att_pipe_min_batch)
         rc = self._lib.tone_create(C.byref(cfg), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

@@ -179,6 +179,38 @@ def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode, ff):
         eng.close()
 
 
+# ---- large-batch kernel forms added in round 2b, forced on at sizes the oracle check can afford: the fused attention
+# block (V projection + P.V + out projection + residual per tile of whole streams; ragged last tile, both frame rates,
+# 400 ms chunks: 9 / 18 streams per tile), feed-forward 1 straight into the residual stream with norm_self_att as a row
+# scale inside the projections (needs >= 2048 rows per lane), and the pipelined depthwise-conv kernel at every size.
+@pytest.mark.parametrize("C,B,att,lazy,dw,ap", [(2400, 600, 1, 1, 1, 1), (3200, 333, 1, 1, 1, 1), (2400, 230, 1, -1, 1, -1),
+                                                (2400, 37, 1, 1, 1, 1), (2400, 600, -1, 1, -1, -1), (3200, 61, -1, -1, 1, 1),
+                                                (2400, 5, -1, -1, 1, 1)])
+def test_large_batch_fused_blocks_match_oracle(weights, tb, C, B, att, lazy, dw, ap):
+    n, D = 3, 6
+    # ap: tone_config.att_pipe_min_batch (recompute attention layers as the pipelined persistent kernel)
+    eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, att_block_min_rows=att, lazy_norm_min_rows=lazy,
+                    dw_pipe_min_batch=dw, att_pipe_min_batch=ap)
+    try:
+        W = orc.to_torch(weights)
+        distinct = tb.synth.telephony_pcm(D, C * n, seed=78)
+        idx = (np.arange(B) * 5) % D
+        pcm = np.ascontiguousarray(distinct[idx])
+        slots = eng.alloc_slots(B)
+        lp, tk = _stream_engine(eng, slots, pcm, C)
+        ref, st = _stream_oracle(W, distinct, C)
+        assert np.isfinite(lp).all()
+        assert _lp_close(lp, ref[:, idx])
+        assert (tk == lp.argmax(-1)).all()
+        _check_tokens(tk, ref[:, idx])
+        flat_ref = orc.pack_state(st).astype(np.float32)
+        probe = np.array([0, 1, B // 2, B - 2, B - 1])
+        got = eng.export_states(slots[probe]).astype(np.float32)
+        assert np.abs(got - flat_ref[idx[probe]]).max() <= ST_TOL
+    finally:
+        eng.close()
+
+
 # ---- BASELINE configs[2] / configs[3] shapes: 1024 streams on one GPU (two lanes of 5120 rows: persistent gated GEMMs,
 # 128-wide tiles everywhere) and 4096 streams (the per-GPU share of 8192 streams on 2 GPUs; 20480 rows per lane).
 # 32 / 40 distinct signals replayed across the batch; every stream must reproduce the oracle's answer for its signal,
