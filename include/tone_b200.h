@@ -85,7 +85,7 @@ typedef struct tone_config {
   int32_t fused_ff_min_rows; /* rows per lane from which the fused feed-forward is used (default 2048)       */
   int32_t att_block_min_rows; /* rows per lane from which a score-sharing attention layer runs as ONE kernel  */
                              /* per tile of whole streams: V projection + P.V + out projection + residual     */
-                             /* (default 4096; -1 = never)                                                    */
+                             /* (experimental, opt-in: default never)                                         */
   int32_t lazy_norm_min_rows; /* rows per lane from which feed-forward 1 adds straight into the residual      */
                              /* stream and norm_self_att becomes a row scale inside the projection GEMMs      */
                              /* (default 4096; -1 = never)                                                    */
@@ -93,6 +93,8 @@ typedef struct tone_config {
                              /* persistent kernel (default 128; -1 = never)                                   */
   int32_t att_pipe_min_batch; /* streams per lane from which the recompute attention layers (0, 7, 14, 15) run */
                              /* as the pipelined persistent kernel (default 256; -1 = never)                  */
+  int32_t persist_ctas;      /* CTAs of a persistent kernel when the step runs in more than one lane          */
+                             /* (default: the SM count; SM count / lanes gives every lane its own SMs)        */
 } tone_config;
 
 #define TONE_FLAG_NO_PDL 1         /* launch the kernels of a step without programmatic dependent launch     */

@@ -37,10 +37,10 @@ constexpr int ATF_THREADS = 320;                 // warp 0: TMA, warp 1: MMA, wa
 constexpr int ATF_KB = 6;                        // K blocks of 64 in d_model
 constexpr int ATF_STAGES = 4;                    // weight ring: 128 rows x 64 k per stage
 constexpr int ATF_TILE = 128 * 128;              // bytes of one operand K block
-constexpr int ATF_VLD = 52;                      // floats per staged v row (16 B aligned, conflict-free for 4 streams per warp)
-constexpr int ATF_VST = 128 * ATF_VLD * 4;       // one staging buffer
+constexpr int ATF_VST = 128 * (2 * 48 + 4) * 4;  // v of two heads, fp32, [128][100]
+constexpr int ATF_PST = 2 * 1600 * 4;            // P blocks of two heads: [2][G][R * R padded to 4] (<= 9 x 172 floats each)
 constexpr int ATF_XP = 388;                      // floats per staged row of the final epilogue
-constexpr int ATF_OPER = ATF_KB * ATF_TILE + ATF_STAGES * ATF_TILE + 2 * ATF_VST;
+constexpr int ATF_OPER = ATF_KB * ATF_TILE + ATF_STAGES * ATF_TILE + ATF_VST + ATF_PST;
 constexpr int ATF_SMEM = ATF_OPER + 2 * 384 * 4 + 256 + 1024;
 static_assert(128 * ATF_XP * 4 <= ATF_OPER, "the x tile is staged over the dead operand buffers");
 static_assert(ATF_SMEM <= 232448, "does not fit");
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                   // A rows, later the ctx tile
   uint8_t* sW = sA + ATF_KB * ATF_TILE;
-  float* vst = reinterpret_cast<float*>(sW + ATF_STAGES * ATF_TILE);   // [2][128][VLD]
+  float* vst = reinterpret_cast<float*>(sW + ATF_STAGES * ATF_TILE);   // [128][100] v of two heads, then the P blocks
   float* s_vec = reinterpret_cast<float*>(smem + ATF_OPER);            // bv[384] | bo[384]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 2 * 384);
   uint64_t* full = bars;                   // [STAGES]
@@ -170,83 +170,141 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
       for (int k = 0; k < a.ss_tiles; ++k) tsum += sp[k];
       rs = 1.0f / (sqrtf(tsum) * 0.05103103630798288f + 1e-8f);
     }
-    float pr[VATT_MAX_T], pn[VATT_MAX_T];
-    auto load_p = [&](int h, float* dst) {
-      const float* pp = a.P + (((size_t)(valid ? b : 0) * N_HEADS + h) * R + t) * R;
-#pragma unroll
-      for (int j = 0; j < VATT_MAX_T; ++j) dst[j] = (valid && j < R) ? __ldg(pp + j) : 0.f;
+    // P.V runs on (stream, head, 8-dim group) units with the stream's R x 8 slice of v in registers: every v element is
+    // read from shared memory once per unit (not once per output row), which is what bounds this phase (a broadcast
+    // LDS.128 costs 4 issue cycles whatever it broadcasts).  Two heads per pass: v of both heads staged in fp32, the
+    // heads' R x R probability blocks of the tile's streams staged beside it.
+    const int RR = R * R, RRP = (RR + 3) & ~3;           // floats per (stream, head) block of P, padded to 16 B
+    float* pst = vst + 128 * (2 * D_HEAD + 4);           // [2 heads][G][RRP] behind the v stage [128][100]
+    constexpr int VL2 = 2 * D_HEAD + 4;                  // floats per staged row: two heads + pad
+    // P blocks of a pass ((head of the pass, stream): RR contiguous floats in global memory) -> pst with 4-byte cp.async,
+    // one block per warp at a time; issued when the stage is free, awaited just before the pass's barrier
+    const int ewp = warp - 2;
+    auto stage_p = [&](int pass) {
+      for (int blk = ewp; blk < 2 * G; blk += 8) {
+        const int hh = blk >= G ? 1 : 0, gg = blk - hh * G;
+        const int bb = tile * G + gg;
+        if (bb < a.B) {
+          const float* src = a.P + ((size_t)bb * N_HEADS + 2 * pass + hh) * RR;
+          float* dst = pst + blk * RRP;
+          for (int x = lane; x < RR; x += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + x)), "l"(src + x) : "memory");
+        }
+      }
+      cp_async_commit();
     };
-    load_p(0, pr);
+    stage_p(0);
     mbar_wait(vacc_full, 0);
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
-    const uint32_t ctx_row = smem_u32(sA) + rt * 128;
+    const uint32_t ctx_base = smem_u32(sA);
+#ifdef TONE_PROF
+    long long tp[5] = {0, 0, 0, 0, 0};
+#define ATF_TS(i) if (pass == 1) tp[i] = clock64()
+#else
+#define ATF_TS(i)
+#endif
 #pragma unroll 1
-    for (int h = 0; h < N_HEADS; ++h) {
-      float* vb = vst + (h & 1) * (128 * ATF_VLD);
+    for (int pass = 0; pass < N_HEADS / 2; ++pass) {
+      ATF_TS(0);
       {
-        // this thread's 24 columns of head h: two 16-wide TMEM loads (the second reaches 8 columns further than needed)
-        const int c0 = h * D_HEAD + 24 * hf;
-        uint32_t r0[16], r1[16];
+        // this thread's 48 columns of the pass: head 2 pass + hf, row rt
+        const int c0 = (2 * pass + hf) * D_HEAD;
+        uint32_t r0[16], r1[16], r2[16];
         tmem_ld16_async(tmem_base + lane_base + c0, r0);
         tmem_ld16_async(tmem_base + lane_base + c0 + 16, r1);
+        tmem_ld16_async(tmem_base + lane_base + c0 + 32, r2);
         tmem_ld_wait();
         tmem_regs_ready16(r0);
         tmem_regs_ready16(r1);
-        float* vr = vb + rt * ATF_VLD + 24 * hf;
+        tmem_regs_ready16(r2);
+        float* vr = vst + rt * VL2 + hf * D_HEAD;
         const float* bb = s_vec + c0;
 #pragma unroll
-        for (int c = 0; c < 24; c += 4) {
+        for (int c = 0; c < 48; c += 4) {
+          const uint32_t* rr = c < 16 ? r0 + c : (c < 32 ? r1 + (c - 16) : r2 + (c - 32));
           float4 o;
-          o.x = fmaf(__uint_as_float(c < 16 ? r0[c] : r1[c - 16]), rs, bb[c]);
-          o.y = fmaf(__uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]), rs, bb[c + 1]);
-          o.z = fmaf(__uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]), rs, bb[c + 2]);
-          o.w = fmaf(__uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]), rs, bb[c + 3]);
+          o.x = fmaf(__uint_as_float(rr[0]), rs, bb[c]);
+          o.y = fmaf(__uint_as_float(rr[1]), rs, bb[c + 1]);
+          o.z = fmaf(__uint_as_float(rr[2]), rs, bb[c + 2]);
+          o.w = fmaf(__uint_as_float(rr[3]), rs, bb[c + 3]);
           *reinterpret_cast<float4*>(vr + c) = o;
         }
       }
-      if (h + 1 < N_HEADS) load_p(h + 1, pn);            // travels while the barrier is reached
-      bar_epilogue();                                    // every row of v_h is staged (also: everybody is past head h - 1)
-      if (valid) {
-        const float* vrow = vb + (g * R) * ATF_VLD + 24 * hf;
-        float acc[24];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+      cp_async_wait_all();
+      ATF_TS(1);
+      bar_epilogue();                                    // v and P of the pass are staged
+      ATF_TS(2);
+      const int nunits = 2 * G * 6;                      // (head of the pass, stream, 8-dim group)
+      for (int u = et; u < nunits; u += EPI_THREADS) {
+        const int hh = u / (G * 6), rem = u - hh * (G * 6), gg = rem / 6, dg = rem - gg * 6;
+        if (tile * G + gg >= a.B) continue;
+        float v[VATT_MAX_T][8];
+        const float* vsrc = vst + (gg * R) * VL2 + hh * D_HEAD + dg * 8;
 #pragma unroll
         for (int j = 0; j < VATT_MAX_T; ++j) {
           if (j < R) {
-            const float p = pr[j];
-#pragma unroll
-            for (int i = 0; i < 24; i += 4) {
-              const float4 v = *reinterpret_cast<const float4*>(vrow + j * ATF_VLD + i);
-              acc[i] = fmaf(p, v.x, acc[i]);
-              acc[i + 1] = fmaf(p, v.y, acc[i + 1]);
-              acc[i + 2] = fmaf(p, v.z, acc[i + 2]);
-              acc[i + 3] = fmaf(p, v.w, acc[i + 3]);
-            }
+            const float4 v0 = *reinterpret_cast<const float4*>(vsrc + j * VL2);
+            const float4 v1 = *reinterpret_cast<const float4*>(vsrc + j * VL2 + 4);
+            v[j][0] = v0.x; v[j][1] = v0.y; v[j][2] = v0.z; v[j][3] = v0.w;
+            v[j][4] = v1.x; v[j][5] = v1.y; v[j][6] = v1.z; v[j][7] = v1.w;
           }
         }
-        // ctx columns [48 h + 24 hf, + 24) of this row: three 16-byte chunks of the swizzled K-major operand tile
+        const float* pp = pst + (hh * G + gg) * RRP;
+        const int chunk = (2 * pass + hh) * 6 + dg;      // 16-byte chunk of the 768-byte ctx row
+        const int kb = chunk >> 3, cc = chunk & 7;
+#pragma unroll 1
+        for (int t = 0; t < R; ++t) {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int chunk = h * 6 + hf * 3 + i;          // 16-byte chunk of the 768-byte row
-          const int kb = chunk >> 3, cc = chunk & 7;
-          sts128u(ctx_row + kb * ATF_TILE + ((cc ^ (rt & 7)) << 4),
-                  make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
-                             pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7])));
+          for (int j = 0; j < VATT_MAX_T; ++j) {
+            if (j < R) {
+              const float p = pp[t * R + j];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, v[j][i], acc[i]);
+            }
+          }
+          const int row = gg * R + t;
+          sts128u(ctx_base + kb * ATF_TILE + row * 128 + ((cc ^ (row & 7)) << 4),
+                  make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                             pack_bf16x2(acc[6], acc[7])));
         }
       }
-#pragma unroll
-      for (int j = 0; j < VATT_MAX_T; ++j) pr[j] = pn[j];
+      ATF_TS(3);
+      bar_epilogue();                                    // the stage is free for the next pass
+      if (pass + 1 < N_HEADS / 2) stage_p(pass + 1);
+      ATF_TS(4);
     }
+#ifdef TONE_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 64 && g_prof)
+      printf("att block R %d: drain %lld barrier1 %lld units %lld barrier2+stage %lld\n", R, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
+#endif
     tc_fence_before();                                   // this warp's TMEM reads are done: the out projection may overwrite
     fence_proxy_async();                                 // generic-proxy writes of the ctx tile -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(ctx_full);
     if (threadIdx.x == 64) PROF_MARK(1);             // head loop done
 
-    // ---- final epilogue.  Phase A (thread = row, columns [192 hf, +192)): acc + bo -> fp32 tile X[128][388] staged over
-    // the operand buffers, which are dead once the last MMA has completed.
+    // ---- final epilogue.  The residual rows of this warp's first batch are requested before the out projection has
+    // finished (they do not depend on it).  Phase A (thread = row, columns [192 hf, +192)): acc + bo -> fp32 tile
+    // X[128][388] staged over the operand buffers, which are dead once the last MMA has completed.  Phase B (warp = 16
+    // rows, lanes along the row, 8 rows in flight): x = r + X -> r, bf16(x) -> rb, sum x^2 -> ss.
+    const int ew = warp - 2;
+    const int nrows = G * R;
+    float4 x[8][3];
+    auto row_ok = [&](int rr) { return rr < nrows && (tile * G + rr / R) < a.B; };
+    auto load_rows = [&](int rg) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = ew * 16 + rg + k;
+        if (row_ok(rr)) {
+          const float* src = a.r + ((size_t)row0 + rr) * D_MODEL;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) x[k][i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        }
+      }
+    };
+    load_rows(0);
     mbar_wait(oacc_full, 0);
     if (threadIdx.x == 64) PROF_MARK(3);             // out projection complete
     tc_fence_after();
@@ -272,50 +330,34 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
       }
     }
     bar_epilogue();
-    // Phase B (warp = 16 rows, lanes along the row): x = r + X -> r, bf16(x) -> rb, sum x^2 -> ss
-    {
-      const int ew = warp - 2;
-      const int nrows = G * R;
 #pragma unroll 1
-      for (int rg = 0; rg < 16; rg += 4) {
-        float4 x[4][3];
-        bool ok[4];
+    for (int rg = 0; rg < 16; rg += 8) {
+      if (rg) load_rows(rg);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                       // four rows of residual in flight
-          const int rr = ew * 16 + rg + k;
-          ok[k] = rr < nrows && (tile * G + rr / R) < a.B;
-          if (ok[k]) {
-            const float* src = a.r + ((size_t)row0 + rr) * D_MODEL;
+      for (int k = 0; k < 8; ++k) {
+        const int rr = ew * 16 + rg + k;
+        if (!row_ok(rr)) continue;                          // warp-uniform
+        const size_t gr = (size_t)row0 + rr;
+        float sq = 0.f;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) x[k][i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
-          }
+        for (int i = 0; i < 3; ++i) {
+          const float4 d = lds128(smem_u32(X) + (rr * ATF_XP + i * 128 + lane * 4) * 4);
+          x[k][i].x += d.x;
+          x[k][i].y += d.y;
+          x[k][i].z += d.z;
+          x[k][i].w += d.w;
+          sq += x[k][i].x * x[k][i].x + x[k][i].y * x[k][i].y + x[k][i].z * x[k][i].z + x[k][i].w * x[k][i].w;
         }
+        float* dst = a.r + gr * D_MODEL;
+        bf16* rb = a.rb_out + gr * D_MODEL;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!ok[k]) continue;                             // warp-uniform
-          const int rr = ew * 16 + rg + k;
-          const size_t gr = (size_t)row0 + rr;
-          float sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float4 d = lds128(smem_u32(X) + (rr * ATF_XP + i * 128 + lane * 4) * 4);
-            x[k][i].x += d.x;
-            x[k][i].y += d.y;
-            x[k][i].z += d.z;
-            x[k][i].w += d.w;
-            sq += x[k][i].x * x[k][i].x + x[k][i].y * x[k][i].y + x[k][i].z * x[k][i].z + x[k][i].w * x[k][i].w;
-          }
-          float* dst = a.r + gr * D_MODEL;
-          bf16* rb = a.rb_out + gr * D_MODEL;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            *reinterpret_cast<float4*>(dst + i * 128 + lane * 4) = x[k][i];
-            *reinterpret_cast<uint2*>(rb + i * 128 + lane * 4) =
-                make_uint2(pack_bf16x2(x[k][i].x, x[k][i].y), pack_bf16x2(x[k][i].z, x[k][i].w));
-          }
-          sq = warp_sum(sq);
-          if (lane == 0) a.ss_out[gr * a.ss_ld] = sq;
+        for (int i = 0; i < 3; ++i) {
+          *reinterpret_cast<float4*>(dst + i * 128 + lane * 4) = x[k][i];
+          *reinterpret_cast<uint2*>(rb + i * 128 + lane * 4) =
+              make_uint2(pack_bf16x2(x[k][i].x, x[k][i].y), pack_bf16x2(x[k][i].z, x[k][i].w));
         }
+        sq = warp_sum(sq);
+        if (lane == 0) a.ss_out[gr * a.ss_ld] = sq;
       }
     }
   }

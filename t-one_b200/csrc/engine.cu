@@ -226,6 +226,8 @@ struct tone_engine {
   // Large dense GEMMs (>= persist_min_tiles output tiles) run as a persistent one-CTA-per-SM kernel with the epilogue
   // overlapped with the next tile's main loop (gemm_tc_persist_kernel); 0 = never.
   int persist_min_tiles = 0, persist_ctas = 0;
+  int lane_ctas = 0;    // persistent-kernel CTAs while a step runs in more than one lane (tone_config.persist_ctas)
+  int cur_ctas = 148;   // CTAs a persistent kernel of the step being enqueued may occupy
   // gated kinds (N % 256 == 0): 0 = 128-wide tiles, 1 = 256-wide, 2 = 256-wide on CTA pairs (cta_group::2).  Measured
   // (profiles/r01_persistent_gemm.md): the pair form runs the feed-forward up GEMM at 73 % of the sustained bf16 peak when
   // it has the GPU to itself, but with two lanes in flight the 256-wide single-CTA form gives the faster step.
@@ -237,7 +239,7 @@ struct tone_engine {
   int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
   // score-sharing attention layers as ONE kernel per tile of whole streams (att_fused.cuh) from this many rows per lane (0 = never)
-  int att_block_min_rows = 4096;
+  int att_block_min_rows = 0;      // opt-in (tone_config.att_block_min_rows): measured slower than the two-kernel form, profiles/r02_experiments.md
   // feed-forward 1 adds straight into the residual stream and norm_self_att becomes a row scale inside the projection
   // GEMMs from this many rows per lane (0 = never)
   int lazy_norm_min_rows = 4096;
@@ -567,6 +569,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_ff_fused<true>()));
   CK(configure_att_fused());
   e->persist_ctas = e->num_sms;
+  e->lane_ctas = cfg->persist_ctas > 0 ? std::min(cfg->persist_ctas, e->num_sms) : e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
   CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_V_SMEM));
@@ -1072,16 +1075,17 @@ static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const W
                                              KIND == G_PARTIAL);
   bool persist = false;
   if constexpr (can_persist)
-    persist = e->cfg.gemm_impl == 0 && splits == 1 && e->persist_min_tiles > 0 && m_tiles * n_tiles >= e->persist_min_tiles;
+    persist = e->cfg.gemm_impl == 0 && splits == 1 && e->persist_min_tiles > 0 &&
+              m_tiles * n_tiles >= std::min(e->persist_min_tiles, e->cur_ctas + 1);
   if (persist) {
     if constexpr (can_persist) {
       const CUtensorMap& mb = box128 ? w.map128 : w.map;
       constexpr bool wide = (KIND == G_SWIGLU || KIND == G_GLU);   // N a multiple of 256: two weight tiles per tile
       if (wide && e->persist_mode == 2)
-        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, wide>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
+        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, wide>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->cur_ctas);
       else if (wide && e->persist_mode == 1)
-        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
-      else err = launch_gemm_tc_persist<KIND, 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->persist_ctas);
+        err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->cur_ctas);
+      else err = launch_gemm_tc_persist<KIND, 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->cur_ctas);
     }
   } else if (e->cfg.gemm_impl == 0)
     err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, box128 ? w.map128 : w.map, a, m_tiles, n_tiles, e->pdl,
@@ -1268,7 +1272,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     a.B = B;
     const int n_mt = (F + 15) / 16, UH = ((16 * n_mt * HOP + HOP + 16) + 7) & ~7;
     const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + ROLL_BYTES + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4;
-    KLAUNCH(launch_kernel(begin_step_kernel, dim3(std::min(B, e->num_sms)), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
+    KLAUNCH(launch_kernel(begin_step_kernel, dim3(std::min(B, e->cur_ctas)), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
   }
   {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels
     GemmArgs a;
@@ -1473,9 +1477,9 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     } else if (RECOMPUTE[l] && e->att_pipe_min_batch > 0 && B >= e->att_pipe_min_batch) {
       const size_t smem = (size_t)ATP_FIXED_SMEM + (size_t)(2 * at.Tk + at.T) * (D_MODEL * 4 + ATP_PAD);
       if (at.S > 0)
-        KLAUNCH(launch_kernel(attention_pipe_kernel<512>, dim3(std::min(B, e->num_sms)), dim3(512), smem, st, e->pdl, at, B));
+        KLAUNCH(launch_kernel(attention_pipe_kernel<512>, dim3(std::min(B, e->cur_ctas)), dim3(512), smem, st, e->pdl, at, B));
       else
-        KLAUNCH(launch_kernel(attention_pipe_kernel<256>, dim3(std::min(B, 2 * e->num_sms)), dim3(256), smem, st, e->pdl, at, B));
+        KLAUNCH(launch_kernel(attention_pipe_kernel<256>, dim3(std::min(B, 2 * e->cur_ctas)), dim3(256), smem, st, e->pdl, at, B));
     } else if (RECOMPUTE[l]) KLAUNCH(launch_kernel(attention_kernel<true>, dim3(B, N_HEADS / ATT_HEADS_REC), dim3(ATT_THREADS_REC), ATT_V_SMEM, st, e->pdl, at));
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
@@ -1502,7 +1506,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.T = Tl;
       const int dw_half = (Tl + 1) / 2;   // output frames per thread
       if (e->dw_pipe_min_batch > 0 && B >= e->dw_pipe_min_batch) {
-        const dim3 grid(std::min(B, 2 * e->num_sms));
+        const dim3 grid(std::min(B, 2 * e->cur_ctas));
         if (Tl <= 5) KLAUNCH(launch_kernel(dwconv_pipe_kernel<5>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
         else if (Tl <= 7) KLAUNCH(launch_kernel(dwconv_pipe_kernel<7>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
         else if (Tl <= 10) KLAUNCH(launch_kernel(dwconv_pipe_kernel<10>, grid, dim3(DWP_THREADS), DWP_SMEM, st, e->pdl, d, B));
@@ -1571,6 +1575,7 @@ enum StepMode : int { SM_FEATURES = 1, SM_PHRASES = 2, SM_PCM16 = 4 };
 static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStream_t st, float* taps, int mode) {
   int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
   nl = std::min(nl, B);
+  e->cur_ctas = nl > 1 ? e->lane_ctas : e->num_sms;
   e->launches = 0;
   const int per = (B + nl - 1) / nl;
   const int pcm_fmt = (mode & SM_PCM16) ? 1 : 0;
