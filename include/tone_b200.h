@@ -93,6 +93,9 @@ typedef struct tone_config {
                              /* persistent kernel (default 128; -1 = never)                                   */
   int32_t att_pipe_min_batch; /* streams per lane from which the recompute attention layers (0, 7, 14, 15) run */
                              /* as the pipelined persistent kernel (default 256; -1 = never)                  */
+  int32_t rowgemm_min_rows;  /* rows per lane from which the N = 384 projections (feed-forward down, attention */
+                             /* out, pointwise conv 2) run as the row-owner CTA-pair kernel with the residual  */
+                             /* add and the norms in its epilogue (default 4096; -1 = never)                   */
   int32_t persist_ctas;      /* CTAs of a persistent kernel when the step runs in more than one lane          */
                              /* (default: the SM count; SM count / lanes gives every lane its own SMs)        */
 } tone_config;

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtone_b200.so")
 SOURCES = ["engine.cu", "server.cu"]
-HEADERS = ["common.cuh", "gemm_tc.cuh", "gemm_ref.cuh", "kernels.cuh", "ctc_phrase.cuh", "state_io.cuh", "ff_fused.cuh", "att_fused.cuh",
+HEADERS = ["common.cuh", "gemm_tc.cuh", "gemm_ref.cuh", "kernels.cuh", "ctc_phrase.cuh", "state_io.cuh", "ff_fused.cuh", "att_fused.cuh", "rowgemm.cuh",
            os.path.join("..", "..", "include", "tone_b200.h")]
 
 

@@ -32,6 +32,7 @@
 #include "ctc_phrase.cuh"
 #include "ff_fused.cuh"
 #include "att_fused.cuh"
+#include "rowgemm.cuh"
 #include "state_io.cuh"
 
 using namespace tone;
@@ -243,6 +244,9 @@ struct tone_engine {
   // feed-forward 1 adds straight into the residual stream and norm_self_att becomes a row scale inside the projection
   // GEMMs from this many rows per lane (0 = never)
   int lazy_norm_min_rows = 4096;
+  // N = 384 projections (feed-forward down, attention out, pointwise conv 2) as the row-owner CTA-pair kernel
+  // (rowgemm.cuh) from this many rows per lane (0 = never)
+  int rowgemm_min_rows = 0;        // opt-in: measured slower (profiles/r02_experiments.md)
   int att_pipe_min_batch = 256;  // streams per lane from which the recompute attention layers run as the pipelined persistent kernel
   int dw_pipe_min_batch = 128;   // streams per lane from which the depthwise conv runs as the pipelined persistent kernel (0 = never)
   int num_sms = 148;
@@ -365,7 +369,7 @@ extern "C" int tone_create(const tone_config* cfg, tone_engine** out) {
   if (cfg->lanes < 0 || cfg->lanes > 4 || cfg->persist_mode < 0 || cfg->persist_mode > 3 || cfg->split_k < 0 ||
       cfg->split_k > MAX_SPLITS || cfg->lane_min_batch < 0 || cfg->fused_ff < 0 || cfg->fused_ff > 3 || cfg->fused_ff_min_rows < 0 ||
       cfg->att_block_min_rows < -1 || cfg->lazy_norm_min_rows < -1 || cfg->dw_pipe_min_batch < -1 ||
-      cfg->att_pipe_min_batch < -1)
+      cfg->att_pipe_min_batch < -1 || cfg->rowgemm_min_rows < -1)
     return fail(TONE_EINVAL, "tuning field out of range (lanes 0..4, persist_mode 0..3, split_k 0..%d)", (int)MAX_SPLITS);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -401,6 +405,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   if (cfg->lazy_norm_min_rows) e->lazy_norm_min_rows = std::max(0, cfg->lazy_norm_min_rows);
   if (cfg->dw_pipe_min_batch) e->dw_pipe_min_batch = std::max(0, cfg->dw_pipe_min_batch);
   if (cfg->att_pipe_min_batch) e->att_pipe_min_batch = std::max(0, cfg->att_pipe_min_batch);
+  if (cfg->rowgemm_min_rows) e->rowgemm_min_rows = std::max(0, cfg->rowgemm_min_rows);
   e->persist_mode = cfg->persist_mode ? cfg->persist_mode - 1 : 1;
   e->split_k = cfg->split_k;
   if (cfg->fused_ff) e->ff_fused = cfg->fused_ff - 1;
@@ -568,6 +573,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   CK((configure_ff_fused<false>()));
   CK((configure_ff_fused<true>()));
   CK(configure_att_fused());
+  CK(configure_rowgemm());
   e->persist_ctas = e->num_sms;
   e->lane_ctas = cfg->persist_ctas > 0 ? std::min(cfg->persist_ctas, e->num_sms) : e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
@@ -1237,6 +1243,40 @@ static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_
   return 0;
 }
 
+// Row-owner CTA-pair GEMM (rowgemm.cuh): x = r + scale * (A W^T + b); r = x or norm(x; g1); then rb / ss (row-scale
+// consumer follows) or n = norm(r; g2) (bf16, optional cache-row scatter).
+static bool use_rowgemm(const tone_engine* e, int M) {
+  return e->cfg.gemm_impl == 0 && e->rowgemm_min_rows > 0 && M >= e->rowgemm_min_rows;
+}
+static int run_rowgemm(tone_engine* e, tone_engine::Lane& ln, cudaStream_t st, int M, int K, const CUtensorMap& mapA,
+                       const WeightMat& w, const float* bias, float scale, float* r, bool emit_rb, const float* g1 = nullptr,
+                       const float* g2 = nullptr, bf16* n = nullptr, bf16* kv = nullptr, int rows_per_stream = 1,
+                       int kv_row_off = 0) {
+  RowGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M;
+  a.nk = K / 64;
+  a.bias = bias;
+  a.scale = scale;
+  a.r = r;
+  a.g1 = g1;
+  a.g2 = g2;
+  a.n = n;
+  a.kv = kv;
+  a.slots = ln.slots;
+  a.rows_per_stream = rows_per_stream;
+  a.kv_row_off = kv_row_off;
+  if (emit_rb) {
+    a.rb_out = ln.rb;
+    a.ss_out = ln.ss;
+    a.ss_ld = 12;
+  }
+  cudaError_t err = launch_rowgemm(st, mapA, w.map128, w.map64, a, (M + 127) / 128, e->pdl);
+  e->launches++;
+  if (err != cudaSuccess) return fail(TONE_ECUDA, "row-owner GEMM launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
 // taps: optional host pointer [17][B*T][384]; when set the step synchronises after every layer (debug only)
 static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t st, float* taps) {
   const int T = e->T, T2 = e->T2, F = e->F, C = e->C;
@@ -1333,11 +1373,29 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     const bool lazy_att = !fused_ff && e->lazy_norm_min_rows > 0 && e->cfg.gemm_impl == 0 && M >= std::max(e->lazy_norm_min_rows, BIG_M) &&
                           l < 14 && (RECOMPUTE[l] || e->fuse_vatt);
     int att_ss_tiles = 0;
+    const bool rowg = !fused_ff && use_rowgemm(e, M);
+    bool ff2_norm_done = false;       // norm_out (+ the next layer's first norm) done by feed-forward 2's down projection
+    bool ff1_norm_done = false;       // the attention input (n, or rb + ss) has already been produced by the down projection
     if (fused_ff) {   // feed-forward 1 + residual + norm_self_att (+ cache-row scatter of layers 14 / 15) in one kernel
       if (l < 14) RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n));
       else
         RC(run_ff_fused(e, ln, st, M, r, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, 0, nullptr, L.n_att, ln.n,
                         l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
+    } else if (rowg) {
+      // up GEMM as usual; the down projection owns whole rows: residual add in its epilogue, then either bf16(r) + sum of
+      // squares for the row-scale projections (layers 0..13) or the normalised rows themselves (layers 14 / 15)
+      GemmArgs ua = dense_args(M, D_MODEL, ln.n, ln.h, D_FF, L.ff1_up_b, 1.f);
+      RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ln.m_n, L.ff1_up, ua, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+      if (lazy_att) {
+        RC(run_rowgemm(e, ln, st, M, D_FF, ln.m_h, L.ff1_down, L.ff1_down_b, 0.5f, r, true));
+        att_ss_tiles = 1;
+      } else if (l < 14) {
+        RC(run_rowgemm(e, ln, st, M, D_FF, ln.m_h, L.ff1_down, L.ff1_down_b, 0.5f, r, false, nullptr, L.n_att, ln.n));
+      } else {
+        RC(run_rowgemm(e, ln, st, M, D_FF, ln.m_h, L.ff1_down, L.ff1_down_b, 0.5f, r, false, nullptr, L.n_att, ln.n,
+                       l == 14 ? e->st_kv14 : e->st_kv15, Tl, l == 14 ? MHSA_S / 2 : MHSA_S));
+      }
+      ff1_norm_done = true;
     } else if (lazy_att) {
       RC(run_ff(e, ln, st, M, L.ff1_up, L.ff1_up_b, L.ff1_down, L.ff1_down_b, &ff, 0, r, &att_ss_tiles));
     } else {
@@ -1355,7 +1413,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     at.recompute = RECOMPUTE[l] ? 1 : 0;
     bool fused_att = false, att_block = false;
     if (l < 14) {
-      if (!fused_ff && !lazy_att) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
+      if (!fused_ff && !lazy_att && !ff1_norm_done) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff));
       at.S = 0;
       at.Tk = Tl;
       if (RECOMPUTE[l]) {
@@ -1435,7 +1493,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     } else {
       const int S = (l == 14) ? MHSA_S / 2 : MHSA_S;
       bf16* kvbuf = (l == 14) ? e->st_kv14 : e->st_kv15;
-      if (!fused_ff) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
+      if (!fused_ff && !ff1_norm_done) RC(run_norm(e, ln, st, r, nullptr, L.n_att, ln.n, M, ff, kvbuf, Tl, S));
       float* qbuf = ln.qkv;
       float* kvout = ln.qkv + (size_t)e->rows_alloc * D_MODEL;
       GemmArgs a = dense_args(M, D_MODEL, ln.n, qbuf, D_MODEL, L.q_b, 1.f);
@@ -1484,7 +1542,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     else KLAUNCH(launch_kernel(attention_kernel<false>, dim3(B), dim3(ATT_THREADS), 0, st, e->pdl, at));
     int ss_tiles = 0;
     if (att_block) ss_tiles = 1;      // the fused kernel owns whole rows: one sum of squares per row
-    else RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles, D_MODEL, 1.f));
+    else if (rowg) {
+      RC(run_rowgemm(e, ln, st, M, D_MODEL, ln.m_ctx, L.wo, L.wo_b, 1.f, r, true));
+      ss_tiles = 1;
+    } else RC(run_resid_rowscale(e, ln, st, M, ln.ctx, ln.m_ctx, L.wo, L.wo_b, r, &ss_tiles, D_MODEL, 1.f));
     // ---- convolution module: norm_conv is applied as a row scale inside the pointwise-conv GEMM (A = bf16(r))
     {
       {
@@ -1515,7 +1576,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       else if (dw_half <= 5) KLAUNCH(launch_kernel(dwconv_kernel<5>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
       else KLAUNCH(launch_kernel(dwconv_kernel<DW_TH>, dim3(B, D_MODEL / DW_CH), dim3(DW_THREADS), 0, st, e->pdl, d));
     }
-    RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles, D_MODEL, 1.f));
+    if (rowg) {
+      RC(run_rowgemm(e, ln, st, M, D_MODEL, ln.m_e, L.pw2, L.pw2_b, 1.f, r, true));
+      ss_tiles = 1;
+    } else RC(run_resid_rowscale(e, ln, st, M, ln.ebuf, ln.m_e, L.pw2, L.pw2_b, r, &ss_tiles, D_MODEL, 1.f));
     // ---- second feed-forward (norm_feed_forward2 as a row scale), norm_out and what follows the layer
     if (fused_ff) {   // feed-forward 2 + residual + norm_out + the next layer's first norm in one kernel
       const float* g1 = l == 14 ? nullptr : L.n_out;
@@ -1523,11 +1587,22 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       bf16* n_out = (l == 6 || l == 14) ? nullptr : ln.n;
       RC(run_ff_fused(e, ln, st, M, r, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, ss_tiles, g1, g2, n_out));
       ff = PartIn();
+    } else if (rowg && l != 14) {
+      // the down projection owns whole rows: residual add, norm_out in place and the next layer's first norm in its epilogue
+      GemmArgs ua = dense_args(M, D_MODEL, ln.rb, ln.h, D_FF, L.ff2_up_b, 1.f);
+      ua.ss = ln.ss;
+      ua.ss_ld = 12;
+      ua.ss_tiles = ss_tiles;
+      RC((gemm<G_SWIGLU, BN_SWIGLU>(e, st, ln.m_rb, L.ff2_up, ua, mt, 2 * D_FF / BN_SWIGLU, M, D_FF)));
+      const float* g2 = (l == 6 || l == 15) ? nullptr : e->L[l + 1].n_ff1;
+      RC(run_rowgemm(e, ln, st, M, D_FF, ln.m_h, L.ff2_down, L.ff2_down_b, 0.5f, r, false, L.n_out, g2, l == 6 ? nullptr : ln.n));
+      ff = PartIn();
+      ff2_norm_done = true;
     } else {
       RC(run_ff(e, ln, st, M, L.ff2_up, L.ff2_up_b, L.ff2_down, L.ff2_down_b, &ff, ss_tiles));
     }
     if (l == 6) {
-      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
+      if (!fused_ff && !ff2_norm_done) RC(run_norm(e, ln, st, r, L.n_out, nullptr, nullptr, M, ff));   // r_full = layer output = residual kept for layer 14
       RedArgs ra{ln.r_full, e->st_red, ln.slots, e->red_dw_w, e->red_dw_b, ln.m_red, T, T2};
       KLAUNCH(launch_kernel(reduction_dw_kernel, dim3(B), dim3(D_MODEL), 0, st, e->pdl, ra));
       const int M2 = B * T2;
@@ -1543,10 +1618,10 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       else KLAUNCH(launch_kernel(upsample_norm_kernel<2>, dim3((B * T + 7) / 8), dim3(256), 0, st, e->pdl, ua));
       RC(tap(1 + l, ln.r_full, B * T));
     } else if (l == 15) {
-      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
+      if (!fused_ff && !ff2_norm_done) RC(run_norm(e, ln, st, r, L.n_out, nullptr, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     } else {
-      if (!fused_ff) RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
+      if (!fused_ff && !ff2_norm_done) RC(run_norm(e, ln, st, r, L.n_out, e->L[l + 1].n_ff1, ln.n, M, ff));
       RC(tap(1 + l, r, M));
     }
   }

@@ -45,7 +45,7 @@ class ToneConfig(C.Structure):
                 ("persist_mode", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32),
                 ("fused_ff", C.c_int32), ("fused_ff_min_rows", C.c_int32), ("att_block_min_rows", C.c_int32),
                 ("lazy_norm_min_rows", C.c_int32), ("dw_pipe_min_batch", C.c_int32), ("att_pipe_min_batch", C.c_int32),
-                ("persist_ctas", C.c_int32)]
+                ("rowgemm_min_rows", C.c_int32), ("persist_ctas", C.c_int32)]
 
 
 class ToneInfo(C.Structure):
@@ -185,12 +185,14 @@ class Engine:
                  device: int = 0, gemm_impl: int = 0, use_graph: bool = True, *, lanes: int = 0, lane_min_batch: int = 0,
                  persist_min_tiles: int = 0, persist_mode: int = 0, split_k: int = 0, flags: int = 0,
                  fused_ff: int = 0, fused_ff_min_rows: int = 0, att_block_min_rows: int = 0, lazy_norm_min_rows: int = 0,
-                 dw_pipe_min_batch: int = 0, att_pipe_min_batch: int = 0, persist_ctas: int = 0):
+                 dw_pipe_min_batch: int = 0, att_pipe_min_batch: int = 0, rowgemm_min_rows: int = 0,
+                 persist_ctas: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = ToneConfig(device, chunk_samples, max_slots, max_batch or max_slots, gemm_impl, int(use_graph),
                          lanes, lane_min_batch, persist_min_tiles, persist_mode, split_k, flags, fused_ff, fused_ff_min_rows,
-                         att_block_min_rows, lazy_norm_min_rows, dw_pipe_min_batch, att_pipe_min_batch, persist_ctas)
+                         att_block_min_rows, lazy_norm_min_rows, dw_pipe_min_batch, att_pipe_min_batch, rowgemm_min_rows,
+                         persist_ctas)
         rc = self._lib.tone_create(C.byref(cfg), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

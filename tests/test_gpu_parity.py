@@ -183,14 +183,16 @@ def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode, ff):
 # block (V projection + P.V + out projection + residual per tile of whole streams; ragged last tile, both frame rates,
 # 400 ms chunks: 9 / 18 streams per tile), feed-forward 1 straight into the residual stream with norm_self_att as a row
 # scale inside the projections (needs >= 2048 rows per lane), and the pipelined depthwise-conv kernel at every size.
-@pytest.mark.parametrize("C,B,att,lazy,dw,ap", [(2400, 600, 1, 1, 1, 1), (3200, 333, 1, 1, 1, 1), (2400, 230, 1, -1, 1, -1),
-                                                (2400, 37, 1, 1, 1, 1), (2400, 600, -1, 1, -1, -1), (3200, 61, -1, -1, 1, 1),
-                                                (2400, 5, -1, -1, 1, 1)])
-def test_large_batch_fused_blocks_match_oracle(weights, tb, C, B, att, lazy, dw, ap):
+@pytest.mark.parametrize("C,B,att,lazy,dw,ap,rg", [(2400, 600, 1, 1, 1, 1, -1), (3200, 333, 1, 1, 1, 1, -1), (2400, 230, 1, -1, 1, -1, -1),
+                                                   (2400, 37, 1, 1, 1, 1, -1), (2400, 600, -1, 1, -1, -1, -1), (3200, 61, -1, -1, 1, 1, -1),
+                                                   (2400, 5, -1, -1, 1, 1, -1), (2400, 600, -1, 1, 1, 1, 1), (3200, 333, -1, -1, 1, 1, 1),
+                                                   (2400, 37, -1, -1, -1, -1, 1), (2400, 230, 1, 1, 1, 1, 1)])
+def test_large_batch_fused_blocks_match_oracle(weights, tb, C, B, att, lazy, dw, ap, rg):
     n, D = 3, 6
-    # ap: tone_config.att_pipe_min_batch (recompute attention layers as the pipelined persistent kernel)
+    # ap: tone_config.att_pipe_min_batch (recompute attention layers as the pipelined persistent kernel); rg:
+    # tone_config.rowgemm_min_rows (N = 384 projections as the row-owner CTA-pair kernel; odd tile counts, ragged tiles)
     eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B, att_block_min_rows=att, lazy_norm_min_rows=lazy,
-                    dw_pipe_min_batch=dw, att_pipe_min_batch=ap)
+                    dw_pipe_min_batch=dw, att_pipe_min_batch=ap, rowgemm_min_rows=rg)
     try:
         W = orc.to_torch(weights)
         distinct = tb.synth.telephony_pcm(D, C * n, seed=78)

@@ -11,7 +11,7 @@ os.environ["TONE_B200_LIB"] = os.path.join(ROOT, "t-one_b200", "libtone_b200_pro
 sys.path.insert(0, ROOT)
 tb = importlib.import_module("t-one_b200")
 
-NAMES = {1: "begin_step", 2: "norm", 3: "upsample_norm", 4: "attention", 5: "dwconv", 6: "reduction_dw", 7: "ff_fused", 8: "att_block"}
+NAMES = {1: "begin_step", 2: "norm", 3: "upsample_norm", 4: "attention", 5: "dwconv", 6: "reduction_dw", 7: "ff_fused", 8: "att_block", 9: "rowgemm"}
 KINDS = ["store_f32", "resid", "swiglu", "glu", "conv0", "conv1", "kv", "decoder", "partial", "glu_dw", "vatt"]
 
 
