@@ -85,7 +85,7 @@ typedef struct tone_config {
   int32_t fused_ff_min_rows; /* rows per lane from which the fused feed-forward is used (default 2048)       */
   int32_t att_block_min_rows; /* rows per lane from which a score-sharing attention layer runs as ONE kernel  */
                              /* per tile of whole streams: V projection + P.V + out projection + residual     */
-                             /* (experimental, opt-in: default never)                                         */
+                             /* (default 16384: pays from ~4096 streams per GPU; -1 = never)                   */
   int32_t lazy_norm_min_rows; /* rows per lane from which feed-forward 1 adds straight into the residual      */
                              /* stream and norm_self_att becomes a row scale inside the projection GEMMs      */
                              /* (default 4096; -1 = never)                                                    */
@@ -95,7 +95,7 @@ typedef struct tone_config {
                              /* as the pipelined persistent kernel (default 256; -1 = never)                  */
   int32_t rowgemm_min_rows;  /* rows per lane from which the N = 384 projections (feed-forward down, attention */
                              /* out, pointwise conv 2) run as the row-owner CTA-pair kernel with the residual  */
-                             /* add and the norms in its epilogue (default 4096; -1 = never)                   */
+                             /* add and the norms in its epilogue (default 8192; -1 = never)                   */
   int32_t persist_ctas;      /* CTAs of a persistent kernel when the step runs in more than one lane          */
                              /* (default: the SM count; SM count / lanes gives every lane its own SMs)        */
 } tone_config;

@@ -240,13 +240,13 @@ struct tone_engine {
   int ff_fused = 0, ff_fused_min_rows = 2048;
   bool fuse_vatt = true;   // score-sharing layers: V projection + P.V in one kernel
   // score-sharing attention layers as ONE kernel per tile of whole streams (att_fused.cuh) from this many rows per lane (0 = never)
-  int att_block_min_rows = 0;      // opt-in (tone_config.att_block_min_rows): measured slower than the two-kernel form, profiles/r02_experiments.md
+  int att_block_min_rows = 16384;  // pays from ~4096 streams per GPU (profiles/r02_experiments.md)
   // feed-forward 1 adds straight into the residual stream and norm_self_att becomes a row scale inside the projection
   // GEMMs from this many rows per lane (0 = never)
   int lazy_norm_min_rows = 4096;
   // N = 384 projections (feed-forward down, attention out, pointwise conv 2) as the row-owner CTA-pair kernel
   // (rowgemm.cuh) from this many rows per lane (0 = never)
-  int rowgemm_min_rows = 0;        // opt-in: measured slower (profiles/r02_experiments.md)
+  int rowgemm_min_rows = 8192;     // pays once a lane's grid of row pairs covers half the SMs (2048+ streams per GPU)
   int att_pipe_min_batch = 256;  // streams per lane from which the recompute attention layers run as the pipelined persistent kernel
   int dw_pipe_min_batch = 128;   // streams per lane from which the depthwise conv runs as the pipelined persistent kernel (0 = never)
   int num_sms = 148;
