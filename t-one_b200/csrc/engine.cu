@@ -147,6 +147,7 @@ struct tone_engine {
   bf16 *st_feat, *st_x1, *st_kv14, *st_kv15, *st_conv;
   float* st_red;
   int* st_len;
+  int* st_cpos;         // [slots][2] ring position (oldest row) of the depthwise-conv caches: full-rate / reduced-rate layers
 
   // phrase splitter state (ctc_phrase.cuh)
   PhSlot* st_ph = nullptr;
@@ -159,7 +160,7 @@ struct tone_engine {
   // Step inputs / outputs, per staging set.  Sets 0 .. PIPE-1 form the ring of tone_submit / tone_wait (PCM int16);
   // set PIPE serves the staged / device-pointer / feature / debug entry points (PCM int16 or int32).
   struct IoSet {
-    int *d_slots = nullptr, *d_tokens = nullptr, *d_len_in = nullptr;
+    int *d_slots = nullptr, *d_tokens = nullptr, *d_len_in = nullptr, *d_cpos_in = nullptr;
     void* d_pcm = nullptr;
     unsigned char* d_last = nullptr;
     float *d_logprobs = nullptr, *d_aux = nullptr;
@@ -210,6 +211,7 @@ struct tone_engine {
     int pcm_fmt;
     const __half* feats;                 // non-null: feature-input mode
     int* len_in;
+    int* cpos_in;                        // [B][2] ring positions of the conv caches seen by this step (full / reduced rate)
     float* lp_out;
     int* tok_out;
     float* aux_out;
@@ -442,6 +444,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   rc |= dev_alloc(e, &e->st_kv14, S * KV_ROWS_MAX * D_MODEL);
   rc |= dev_alloc(e, &e->st_kv15, S * KV_ROWS_MAX * D_MODEL);
   rc |= dev_alloc(e, &e->st_conv, S * N_LAYERS * CONV_S * D_MODEL);
+  rc |= dev_alloc(e, &e->st_cpos, S * 2);
   rc |= dev_alloc(e, &e->st_red, S * D_MODEL);
   rc |= dev_alloc(e, &e->st_len, S);
   rc |= dev_alloc(e, &e->st_ph, S);
@@ -464,6 +467,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
     rc |= dev_alloc(e, (char**)&io.d_pcm, pcm_bytes);
     rc |= dev_alloc(e, &io.d_last, Bm);
     rc |= dev_alloc(e, &io.d_len_in, Bm);
+    rc |= dev_alloc(e, &io.d_cpos_in, 2 * Bm);
     rc |= dev_alloc(e, &io.d_tokens, R);
     rc |= dev_alloc(e, &io.d_aux, R * 2);
     rc |= dev_alloc(e, &io.d_logprobs, R * N_CLASSES);
@@ -994,6 +998,7 @@ static StatePool state_pool(tone_engine* e) {
   p.conv = e->st_conv;
   p.red = e->st_red;
   p.len = e->st_len;
+  p.cpos = e->st_cpos;
   p.ph = e->st_ph;
   p.F = e->F;
   p.T = e->T;
@@ -1300,6 +1305,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     a.kv15 = e->st_kv15;
     a.mhsa_len = e->st_len;
     a.len_in = ln.len_in;
+    a.cpos = e->st_cpos;
+    a.cpos_in = ln.cpos_in;
     a.basis = e->basis;
     a.mel_start = e->mel_start;
     a.mel_bin = e->mel_bin;
@@ -1561,6 +1568,7 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
       d.cache = e->st_conv + (size_t)l * CONV_S * D_MODEL;
       d.cache_slot_stride = (long long)N_LAYERS * CONV_S * D_MODEL;
       d.slots = ln.slots;
+      d.cpos_in = ln.cpos_in + (reduced ? 1 : 0);
       d.w = L.dw_w;
       d.bias = L.dw_b;
       d.e = ln.ebuf;
@@ -1664,6 +1672,7 @@ static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStrea
     ln.pcm_fmt = pcm_fmt;
     ln.feats = (mode & SM_FEATURES) ? e->d_feats + (size_t)b0 * N_MELS * e->F : nullptr;
     ln.len_in = io.d_len_in + b0;
+    ln.cpos_in = io.d_cpos_in + 2 * b0;
     ln.lp_out = io.d_logprobs + (size_t)b0 * e->T * N_CLASSES;
     ln.tok_out = io.d_tokens + (size_t)b0 * e->T;
     ln.aux_out = io.d_aux + (size_t)b0 * e->T * 2;

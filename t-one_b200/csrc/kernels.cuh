@@ -43,6 +43,8 @@ struct BeginArgs {
   bf16* kv15;                // [slots][KV_ROWS_MAX][384]   layer-15 [cache | new] rows (30 + T)
   int* mhsa_len;             // [slots]
   int* len_in;               // [B] length seen by this step's masks (value entering the step)
+  int* cpos;                 // [slots][2] ring positions of the depthwise-conv caches (full / reduced rate)
+  int* cpos_in;              // [B][2] positions seen by this step
   const __half* basis;       // [2][168][168] fp16 hi / lo split of the fused pre-emphasis * Hann * DFT basis, row n =
                              // cos bin n (n < 81) / -sin bin n-81, k contiguous, zero padded
   const int* mel_start;      // [65] CSR over mel filters
@@ -165,6 +167,11 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
       int len = a.mhsa_len[slot];
       a.len_in[b] = len;
       a.mhsa_len[slot] = min(len + a.T, MHSA_S);   // conformer_blocks.py:191
+      const int p0 = a.cpos[2 * slot], p1 = a.cpos[2 * slot + 1];
+      a.cpos_in[2 * b] = p0;
+      a.cpos_in[2 * b + 1] = p1;
+      a.cpos[2 * slot] = (p0 + a.T) % CONV_S;      // the T (T2) oldest cache rows are replaced by this step's rows
+      a.cpos[2 * slot + 1] = (p1 + a.T2) % CONV_S;
     }
     if (!a.feats_in)
       for (int i = tid; i < HOP; i += BEGIN_THREADS) pre[i] = uh[C + i];
@@ -998,9 +1005,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
 // ------------------------------------------------------------------------------------------------ depthwise conv
 struct DwArgs {
   const bf16* g;        // [B*T][384] GLU output of this layer
-  bf16* cache;          // [slots][16][30][384] (layer offset already applied), time-major
+  bf16* cache;          // [slots][16][30][384] (layer offset already applied), time-major ring: logical row i (0 = oldest)
+                        // sits at physical row (pos + i) mod 30; a step overwrites its T oldest rows and advances pos by T
   long long cache_slot_stride;
   const int* slots;
+  const int* cpos_in;   // [B][2] (rate offset applied): physical row of the oldest cached frame (the cache is a ring)
   const float* w;       // [31][384] BN-folded taps
   const float* bias;    // [384]     BN-folded bias
   bf16* e;              // [B*T][384]
@@ -1037,6 +1046,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
   bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride + c0;
+  const int pos = a.cpos_in[2 * b];
   {
     const bf16* g = a.g + (size_t)b * T * D_MODEL + c0;
     uint4* t4 = reinterpret_cast<uint4*>(&tile[0][0]);
@@ -1047,7 +1057,8 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
       const int i = tid + k * DW_THREADS;
       if (i < n_all) {
         const int r = i / DW_RV, v = i - r * DW_RV;
-        tmp[k] = (i < n_cache) ? *reinterpret_cast<const uint4*>(cache + (size_t)r * D_MODEL + v * 8)
+        const int pr = r + pos >= CONV_S ? r + pos - CONV_S : r + pos;        // ring: logical row r -> physical row
+        tmp[k] = (i < n_cache) ? *reinterpret_cast<const uint4*>(cache + (size_t)pr * D_MODEL + v * 8)
                                : *reinterpret_cast<const uint4*>(g + (size_t)(r - CONV_S) * D_MODEL + v * 8);
       }
     }
@@ -1079,16 +1090,14 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const DwArgs a) {
 #pragma unroll
   for (int t = 0; t < TH; ++t)
     if (t < half && t0 + t < T) a.e[(size_t)(b * T + t0 + t) * D_MODEL + c] = __float2bfloat16(silu_f(acc[t]));
-  // new cache = last 30 rows of [cache | g]
+  // new cache = last 30 rows of [cache | g]: the T new rows replace the T oldest rows of the ring
   {
-    const uint4* t4 = reinterpret_cast<const uint4*>(&tile[T][0]);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = tid + k * DW_THREADS;
-      if (i < CONV_S * DW_RV) {
-        const int r = i / DW_RV, v = i - r * DW_RV;
-        *reinterpret_cast<uint4*>(cache + (size_t)r * D_MODEL + v * 8) = t4[i];
-      }
+    const uint4* t4 = reinterpret_cast<const uint4*>(&tile[CONV_S][0]);
+    const int i = tid;
+    if (i < T * DW_RV) {
+      const int r = i / DW_RV, v = i - r * DW_RV;
+      const int pr = r + pos >= CONV_S ? r + pos - CONV_S : r + pos;
+      *reinterpret_cast<uint4*>(cache + (size_t)pr * D_MODEL + v * 8) = t4[i];
     }
   }
   PROF_END();
@@ -1127,11 +1136,15 @@ __global__ void __launch_bounds__(DWP_THREADS, 2) dwconv_pipe_kernel(const DwArg
   constexpr uint32_t CACHE_BYTES = CONV_S * D_MODEL * 2;
   const uint32_t g_bytes = (uint32_t)T * D_MODEL * 2;
   const int nmine = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  constexpr uint32_t ROW_BYTES = D_MODEL * 2;
   auto issue = [&](int k) {
     const int b = blockIdx.x + k * gridDim.x, s = k % DWP_STAGES;
     unsigned char* tile = dsm + s * DWP_STAGE_BYTES;
+    const bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride;
+    const int pos = a.cpos_in[2 * b];            // ring: physical rows [pos, 30) are the oldest, then [0, pos)
     mbar_expect_tx(&full[s], CACHE_BYTES + g_bytes);
-    bulk_load_1d(tile, a.cache + (size_t)a.slots[b] * a.cache_slot_stride, CACHE_BYTES, &full[s]);
+    bulk_load_1d(tile, cache + (size_t)pos * D_MODEL, (CONV_S - pos) * ROW_BYTES, &full[s]);
+    if (pos) bulk_load_1d(tile + (CONV_S - pos) * ROW_BYTES, cache, pos * ROW_BYTES, &full[s]);
     bulk_load_1d(tile + CACHE_BYTES, a.g + (size_t)b * T * D_MODEL, g_bytes, &full[s]);
   };
   if (tid == 0)
@@ -1163,8 +1176,13 @@ __global__ void __launch_bounds__(DWP_THREADS, 2) dwconv_pipe_kernel(const DwArg
     for (int t = 0; t < TM; ++t)
       if (t < T) eo[t * D_MODEL] = __float2bfloat16(silu_f(acc[t]));
     __syncthreads();                                      // every thread is done reading the tile
-    if (tid == 0) {                                       // new cache = last 30 rows of [cache | g]
-      bulk_store_1d(a.cache + (size_t)a.slots[b] * a.cache_slot_stride, dsm + s * DWP_STAGE_BYTES + g_bytes, CACHE_BYTES);
+    if (tid == 0) {                                       // the T new rows replace the T oldest rows of the ring
+      bf16* cache = a.cache + (size_t)a.slots[b] * a.cache_slot_stride;
+      const unsigned char* gsm = dsm + s * DWP_STAGE_BYTES + CACHE_BYTES;
+      const int pos = a.cpos_in[2 * b];
+      const int n0 = min(T, CONV_S - pos);
+      bulk_store_1d(cache + (size_t)pos * D_MODEL, gsm, n0 * ROW_BYTES);
+      if (n0 < T) bulk_store_1d(cache, gsm + n0 * ROW_BYTES, (T - n0) * ROW_BYTES);
       bulk_commit();
     }
   }

@@ -18,6 +18,7 @@ struct StatePool {
   bf16* conv;       // [slots][16][30][384]
   float* red;       // [slots][384]
   int* len;         // [slots]
+  int* cpos;        // [slots][2] ring positions of the conv caches (full-rate layers 0..6, 15 | reduced-rate layers 7..14)
   PhSlot* ph;       // [slots]
   int F, T, T2;
 };
@@ -50,6 +51,8 @@ __global__ void __launch_bounds__(STATE_IO_THREADS) reset_slots_kernel(StatePool
   zero_bytes(p.red + s * D_MODEL, D_MODEL * 4, tid, nt);
   if (tid == 0) {
     p.len[s] = 0;
+    p.cpos[2 * s] = 0;
+    p.cpos[2 * s + 1] = 0;
     PhSlot z;
     z.head = 0;
     z.n = 0;
@@ -79,7 +82,9 @@ __global__ void __launch_bounds__(STATE_IO_THREADS) export_state_kernel(StatePoo
       else v = bf2h(p.kv15[(s * KV_ROWS_MAX + p.T + r) * D_MODEL + c]);
     } else if (i < st_off::len) {
       const int j = i - st_off::conv, l = j / (D_MODEL * CONV_S), c = (j / CONV_S) % D_MODEL, t = j % CONV_S;
-      v = bf2h(p.conv[((s * 16 + l) * CONV_S + t) * D_MODEL + c]);
+      // the cache is a ring: logical row t (0 = oldest) sits at physical row (pos + t) mod 30
+      const int pos = p.cpos[2 * s + ((l > 6 && l <= 14) ? 1 : 0)];
+      v = bf2h(p.conv[((s * 16 + l) * CONV_S + (pos + t) % CONV_S) * D_MODEL + c]);
     } else if (i < st_off::sub1) {
       v = __float2half_rn((float)p.len[s]);
     } else if (i < st_off::sub2) {
@@ -115,6 +120,8 @@ __global__ void __launch_bounds__(STATE_IO_THREADS) import_state_kernel(StatePoo
     } else if (i < st_off::sub1) {
       int len = (int)lrintf(__half2float(v));
       p.len[s] = max(0, min(len, MHSA_S));
+      p.cpos[2 * s] = 0;                   // imported caches are stored in logical order
+      p.cpos[2 * s + 1] = 0;
     } else if (i < st_off::sub2) {
       p.feat[(s * FEAT_ROWS_MAX + p.F) * N_MELS + (i - st_off::sub1)] = h2bf(v);
     } else if (i < st_off::red) {
