@@ -431,35 +431,59 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
     bar_epilogue();   // both halves of every row are staged
 
     // ---- phase 2: coalesced write-out of this warp's 16 rows
+    if constexpr (KIND == G_RESID) {
+      // All rows of the warp go through every step together (staging loads, adds, stores, the sum-of-squares shuffles):
+      // walking them one row at a time is a chain of ~16 x (LDS -> FADD -> STG, 5 dependent shuffles) latencies with two
+      // warps per scheduler to hide them.
+      float sq[O::NIT];
+      bool ok[O::NIT];
+      long long orow[O::NIT];
 #pragma unroll
-    for (int it = 0; it < O::NIT; ++it) {
-      const int row = row0 + it * O::RPI + sub_row;
-      const RowInfo ri = row_info<KIND>(a, row);
-      if constexpr (KIND == G_RESID) {
-        float sq = 0.f;
+      for (int it = 0; it < O::NIT; ++it) {
+        const int row = row0 + it * O::RPI + sub_row;
+        const RowInfo ri = row_info<KIND>(a, row);
+        ok[it] = ri.valid;
+        orow[it] = ri.out_row;
+        const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
+        float4 o = ri.valid ? rres[it] : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x += d.x;
+        o.y += d.y;
+        o.z += d.z;
+        o.w += d.w;
+        rres[it] = o;
+        sq[it] = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+      }
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        if (ok[it]) {
+          RowInfo ri;
+          ri.valid = true;
+          ri.out_row = orow[it];
+          *reinterpret_cast<float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb) = rres[it];
+          if (a.rb_out)
+            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
+                make_uint2(pack_bf16x2(rres[it].x, rres[it].y), pack_bf16x2(rres[it].z, rres[it].w));
+        }
+      }
+      if (a.rb_out) {   // reduce every row's LPR lanes; lane 0 of each row group stores the tile's sum
+#pragma unroll
+        for (int off = O::LPR / 2; off > 0; off >>= 1) {
+#pragma unroll
+          for (int it = 0; it < O::NIT; ++it) sq[it] += __shfl_xor_sync(0xffffffffu, sq[it], off);
+        }
+#pragma unroll
+        for (int it = 0; it < O::NIT; ++it)
+          if (ok[it] && (lane % O::LPR) == 0) a.ss_out[orow[it] * a.ss_ld + blockIdx.y] = sq[it];
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        const int row = row0 + it * O::RPI + sub_row;
+        const RowInfo ri = row_info<KIND>(a, row);
         if (ri.valid) {
           char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-          const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
-          float4 o = rres[it];
-          o.x += d.x;
-          o.y += d.y;
-          o.z += d.z;
-          o.w += d.w;
-          *reinterpret_cast<float4*>(dst) = o;
-          if (a.rb_out) {
-            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
-                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-            sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-          }
+          *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
         }
-        if (a.rb_out) {   // warp-uniform: reduce the row's LPR lanes, lane 0 of each row group stores the tile's sum
-#pragma unroll
-          for (int off = O::LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-          if (ri.valid && (lane % O::LPR) == 0) a.ss_out[ri.out_row * a.ss_ld + blockIdx.y] = sq;
-        }
-      } else if (ri.valid) {
-        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-        *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
       }
     }
   }
@@ -773,35 +797,59 @@ __device__ __forceinline__ void epilogue_p(const GemmArgs& a, uint32_t tmem_row_
     bar_epilogue_p(bar_id);   // both halves of every row are staged
 
     // ---- phase 2: coalesced write-out of this warp's 16 rows
+    if constexpr (KIND == G_RESID) {
+      // All rows of the warp go through every step together (staging loads, adds, stores, the sum-of-squares shuffles):
+      // walking them one row at a time is a chain of ~16 x (LDS -> FADD -> STG, 5 dependent shuffles) latencies with two
+      // warps per scheduler to hide them.
+      float sq[O::NIT];
+      bool ok[O::NIT];
+      long long orow[O::NIT];
 #pragma unroll
-    for (int it = 0; it < O::NIT; ++it) {
-      const int row = row0 + it * O::RPI + sub_row;
-      const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, row);
-      if constexpr (KIND == G_RESID) {
-        float sq = 0.f;
+      for (int it = 0; it < O::NIT; ++it) {
+        const int row = row0 + it * O::RPI + sub_row;
+        const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, row);
+        ok[it] = ri.valid;
+        orow[it] = ri.out_row;
+        const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
+        float4 o = ri.valid ? rres[it] : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x += d.x;
+        o.y += d.y;
+        o.z += d.z;
+        o.w += d.w;
+        rres[it] = o;
+        sq[it] = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+      }
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        if (ok[it]) {
+          RowInfo ri;
+          ri.valid = true;
+          ri.out_row = orow[it];
+          *reinterpret_cast<float4*>(out_row_ptr<KIND>(a, ri, n0_out) + cb) = rres[it];
+          if (a.rb_out)
+            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
+                make_uint2(pack_bf16x2(rres[it].x, rres[it].y), pack_bf16x2(rres[it].z, rres[it].w));
+        }
+      }
+      if (a.rb_out) {   // reduce every row's LPR lanes; lane 0 of each row group stores the tile's sum
+#pragma unroll
+        for (int off = O::LPR / 2; off > 0; off >>= 1) {
+#pragma unroll
+          for (int it = 0; it < O::NIT; ++it) sq[it] += __shfl_xor_sync(0xffffffffu, sq[it], off);
+        }
+#pragma unroll
+        for (int it = 0; it < O::NIT; ++it)
+          if (ok[it] && (lane % O::LPR) == 0) a.ss_out[orow[it] * a.ss_ld + ty] = sq[it];
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < O::NIT; ++it) {
+        const int row = row0 + it * O::RPI + sub_row;
+        const RowInfo ri = row_info_p<KIND, PERSIST>(a, tx, row);
         if (ri.valid) {
           char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-          const float4 d = lds128(smem_u32(stage) + row * O::STRIDE + cb);
-          float4 o = rres[it];
-          o.x += d.x;
-          o.y += d.y;
-          o.z += d.z;
-          o.w += d.w;
-          *reinterpret_cast<float4*>(dst) = o;
-          if (a.rb_out) {
-            *reinterpret_cast<uint2*>(a.rb_out + ri.out_row * a.ldo + n0_out + cb / 4) =
-                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-            sq = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-          }
+          *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
         }
-        if (a.rb_out) {   // warp-uniform: reduce the row's LPR lanes, lane 0 of each row group stores the tile's sum
-#pragma unroll
-          for (int off = O::LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-          if (ri.valid && (lane % O::LPR) == 0) a.ss_out[ri.out_row * a.ss_ld + ty] = sq;
-        }
-      } else if (ri.valid) {
-        char* dst = out_row_ptr<KIND>(a, ri, n0_out) + cb;
-        *reinterpret_cast<uint4*>(dst) = lds128u(smem_u32(stage) + row * O::STRIDE + cb);
       }
     }
   }
