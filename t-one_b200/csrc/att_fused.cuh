@@ -198,15 +198,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
     const uint32_t ctx_base = smem_u32(sA);
-#ifdef TONE_PROF
-    long long tp[5] = {0, 0, 0, 0, 0};
-#define ATF_TS(i) if (pass == 1) tp[i] = clock64()
-#else
-#define ATF_TS(i)
-#endif
 #pragma unroll 1
     for (int pass = 0; pass < N_HEADS / 2; ++pass) {
-      ATF_TS(0);
       {
         // this thread's 48 columns of the pass: head 2 pass + hf, row rt
         const int c0 = (2 * pass + hf) * D_HEAD;
@@ -232,9 +225,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
         }
       }
       cp_async_wait_all();
-      ATF_TS(1);
       bar_epilogue();                                    // v and P of the pass are staged
-      ATF_TS(2);
       const int nunits = 2 * G * 6;                      // (head of the pass, stream, 8-dim group)
       for (int u = et; u < nunits; u += EPI_THREADS) {
         const int hh = u / (G * 6), rem = u - hh * (G * 6), gg = rem / 6, dg = rem - gg * 6;
@@ -270,15 +261,9 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) att_fused_kernel(const __grid_
                              pack_bf16x2(acc[6], acc[7])));
         }
       }
-      ATF_TS(3);
       bar_epilogue();                                    // the stage is free for the next pass
       if (pass + 1 < N_HEADS / 2) stage_p(pass + 1);
-      ATF_TS(4);
     }
-#ifdef TONE_PROF
-    if (blockIdx.x == 0 && threadIdx.x == 64 && g_prof)
-      printf("att block R %d: drain %lld barrier1 %lld units %lld barrier2+stage %lld\n", R, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
-#endif
     tc_fence_before();                                   // this warp's TMEM reads are done: the out projection may overwrite
     fence_proxy_async();                                 // generic-proxy writes of the ctx tile -> visible to the tensor core
     __syncwarp();

@@ -210,30 +210,28 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
     }
     return;
   } else if constexpr (KIND == G_VATT) {
-    // Tile = G whole streams x R frames (rows), one head (48 columns).  Phase 1: v rows (+ bias) -> fp32 staging.
+    // Tile = G whole streams x R frames (rows), one head (48 columns).  Phase 1: v rows (+ bias) -> fp32 staging, and the
+    // tile's probability blocks (one contiguous R x R block per stream and head) -> shared memory beside them.
     // Phase 2: unit = (row, 8 dims): ctx[t][d] = sum_j P[t][j] v[j][d] over the R rows of the row's stream.
     static_assert(KIND != G_VATT || BN == 48, "one head per tile");
     constexpr int VLD = 52;                              // floats per staged v row (16 B aligned, conflict-light)
-    const int R = a.R, head = blockIdx.y;
+    const int R = a.R, head = blockIdx.y, RR = R * R;
     float* vst = reinterpret_cast<float*>(stage);
-    // P rows of this thread's units, fetched before the accumulator is ready (they come from an earlier layer)
-    constexpr int NU = 3;                                // units per thread: 128 rows x 6 / 256 threads
+    float* pst = vst + 128 * VLD;                        // [G][R * R]
     const int et = (threadIdx.x - 64);
-    float pr[NU][VATT_MAX_T];
-    int urow[NU], uu[NU];
-    bool uok[NU];
+    // This thread's share of the P blocks, fetched (coalesced: consecutive threads, consecutive floats of a block) before
+    // the accumulator is ready - they come from an earlier layer.  A per-unit gather of P rows (39 scalar loads per thread,
+    // ~5000 sector requests per CTA) used to be what bound this epilogue.
+    constexpr int NP = (128 * VATT_MAX_T + EPI_THREADS - 1) / EPI_THREADS;   // G * R * R <= 128 * 13
+    float pre[NP];
+    const int np = a.G * RR, b0 = blockIdx.x * a.G;
 #pragma unroll
-    for (int k = 0; k < NU; ++k) {
-      const int unit = et + k * EPI_THREADS;
-      urow[k] = unit / 6;
-      uu[k] = unit - urow[k] * 6;
-      const RowInfo ri = row_info<KIND>(a, urow[k] < 128 ? urow[k] : 0);
-      uok[k] = urow[k] < 128 && ri.valid;
-      if (uok[k]) {
-        const int b = (int)(ri.out_row / R), t = (int)(ri.out_row - (long long)b * R);
-        const float* pp = a.P + (((size_t)b * 8 + head) * R + t) * R;
-#pragma unroll
-        for (int j = 0; j < VATT_MAX_T; ++j) pr[k][j] = j < R ? __ldg(pp + j) : 0.f;
+    for (int i = 0; i < NP; ++i) {
+      const int e = et + i * EPI_THREADS;
+      pre[i] = 0.f;
+      if (e < np) {
+        const int g = e / RR, x = e - g * RR;
+        if (b0 + g < a.M) pre[i] = __ldg(a.P + ((size_t)(b0 + g) * 8 + head) * RR + x);
       }
     }
     // row-scale RMSNorm folded around the V projection (A = bf16 residual rows, gain folded into the weights)
@@ -258,7 +256,7 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
       tmem_ld_wait();
       tmem_regs_ready16(r0);
       tmem_regs_ready16(r1);
-      float* vr = vst + (q * 32 + lane) * VLD + 24 * hf;
+      const uint32_t vr = smem_u32(vst) + ((q * 32 + lane) * VLD + 24 * hf) * 4;
 #pragma unroll
       for (int c = 0; c < 24; c += 4) {
         float4 o;
@@ -266,32 +264,60 @@ __device__ __forceinline__ void epilogue(const GemmArgs& a, uint32_t tmem_row_ba
         o.y = fmaf(__uint_as_float(c + 1 < 16 ? r0[c + 1] : r1[c + 1 - 16]), rsv, s_c0[24 * hf + c + 1]);
         o.z = fmaf(__uint_as_float(c + 2 < 16 ? r0[c + 2] : r1[c + 2 - 16]), rsv, s_c0[24 * hf + c + 2]);
         o.w = fmaf(__uint_as_float(c + 3 < 16 ? r0[c + 3] : r1[c + 3 - 16]), rsv, s_c0[24 * hf + c + 3]);
-        *reinterpret_cast<float4*>(vr + c) = o;
+        sts128(vr + c * 4, o);
       }
     }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int e = et + i * EPI_THREADS;
+      if (e < np) sts32(smem_u32(pst) + e * 4, pre[i]);
+    }
     bar_epilogue();
+    // unit = (stream, 8-dim group, half of the stream's frames when R > 7): every v element is read once per unit, not
+    // once per output row - shared-memory read bandwidth (a 32-lane LDS.128 returns 512 B whatever it broadcasts) is what
+    // bounds this phase, and two CTAs share an SM
+    {
+      const int nth = R > 7 ? 2 : 1, rows_u = (R + nth - 1) / nth;           // frames per unit: <= 7
+      const int nunits = a.G * 6 * nth;
+      for (int unit = et; unit < nunits; unit += EPI_THREADS) {
+        const int g = unit / (6 * nth), rem = unit - g * (6 * nth), uu = rem / nth, th = rem - uu * nth;
+        if (b0 + g >= a.M) continue;
+        const int t0 = th * rows_u;
+        // shared-window addresses (generic pointers cost 64-bit address arithmetic and LD.E per access)
+        uint32_t va = smem_u32(vst) + ((g * R) * VLD + uu * 8) * 4;
+        uint32_t pa = smem_u32(pst) + (g * RR + t0 * R) * 4;
+        float acc[7][8];
 #pragma unroll
-    for (int k = 0; k < NU; ++k) {
-      if (!uok[k]) continue;
-      const int g = urow[k] / R;                          // stream within the tile
-      const float* vb = vst + (g * R) * VLD + uu[k] * 8;
-      float acc[8];
+        for (int t = 0; t < 7; ++t)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+        const int nrows = min(rows_u, R - t0);
+        // All seven row slots are computed (rows beyond nrows read whatever follows in the staging area and are never
+        // stored): no branches in the loop, and the seven P loads of a step are issued together ahead of the FMAs.
+        const uint32_t r4 = (uint32_t)R * 4;
+#pragma unroll 2
+        for (int j = 0; j < R; ++j, va += VLD * 4, pa += 4) {
+          const float4 v0 = lds128(va), v1 = lds128(va + 16);
+          float pv[7];
 #pragma unroll
-      for (int j = 0; j < VATT_MAX_T; ++j) {
-        if (j < R) {
-          const float4 v0 = *reinterpret_cast<const float4*>(vb + j * VLD);
-          const float4 v1 = *reinterpret_cast<const float4*>(vb + j * VLD + 4);
-          const float p = pr[k][j];
-          acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
-          acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+          for (int t = 0; t < 7; ++t) pv[t] = lds32(pa + t * r4);
+#pragma unroll
+          for (int t = 0; t < 7; ++t) {
+            const float p = pv[t];
+            acc[t][0] = fmaf(p, v0.x, acc[t][0]); acc[t][1] = fmaf(p, v0.y, acc[t][1]);
+            acc[t][2] = fmaf(p, v0.z, acc[t][2]); acc[t][3] = fmaf(p, v0.w, acc[t][3]);
+            acc[t][4] = fmaf(p, v1.x, acc[t][4]); acc[t][5] = fmaf(p, v1.y, acc[t][5]);
+            acc[t][6] = fmaf(p, v1.z, acc[t][6]); acc[t][7] = fmaf(p, v1.w, acc[t][7]);
+          }
         }
+        bf16* dst = reinterpret_cast<bf16*>(a.out) + ((long long)(b0 + g) * R + t0) * a.ldo + head * 48 + uu * 8;
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+          if (t < nrows)
+            *reinterpret_cast<uint4*>(dst + (long long)t * a.ldo) =
+                make_uint4(pack_bf16x2(acc[t][0], acc[t][1]), pack_bf16x2(acc[t][2], acc[t][3]), pack_bf16x2(acc[t][4], acc[t][5]),
+                           pack_bf16x2(acc[t][6], acc[t][7]));
       }
-      const RowInfo ri = row_info<KIND>(a, urow[k]);
-      bf16* dst = reinterpret_cast<bf16*>(a.out) + ri.out_row * (long long)a.ldo + head * 48 + uu[k] * 8;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
     }
     return;
   } else {

@@ -866,18 +866,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
     issue_v(0);
   }
   const int nk = Tk * N_HEADS, nq = T * N_HEADS;
-#ifdef TONE_PROF
-  long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define ATP_TS(i) if (k == 1) tp[i] = clock64()
-#else
-#define ATP_TS(i)
-#endif
   for (int k = 0; k < nmine; ++k) {
     const int b = blockIdx.x + k * gridDim.x;
-    ATP_TS(0);
     mbar_wait(&kq_full, k & 1);
-    ATP_TS(1);
-    if (k == 1 && threadIdx.x == 0) PROF_MARK(1);
     // ---- per-head LayerNorm + RoPE: key rows stay in registers, query rows go to shared memory (items beyond the
     // thread count of the 256-thread form take a second pass)
     float kx[D_HEAD];
@@ -898,8 +889,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
       for (int d = 0; d < D_HEAD; d += 4) qs[(t * (D_HEAD / 4) + (d >> 2)) * N_HEADS + h] = make_float4(qx[d], qx[d + 1], qx[d + 2], qx[d + 3]);
     }
     __syncthreads();                                         // k / q rows are in registers / qs: their buffers are free
-    ATP_TS(2);
-    if (k == 1 && threadIdx.x == 0) PROF_MARK(3);
     if (warp == 0 && k + 1 < nmine) issue_kq(k + 1);
     int off = 0;
     if (a.mask_mode == 1) off = MHSA_S - a.len_in[b];
@@ -920,7 +909,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
       }
     }
     __syncthreads();
-    ATP_TS(3);
     // ---- masked softmax: 8 lanes per (head, query) row; P is published for the score-sharing layers
     {
       float* Pg = a.P + (size_t)b * N_HEADS * T * Tk;
@@ -960,11 +948,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
       }
     }
     __syncthreads();
-    if (k == 1 && threadIdx.x == 0) PROF_MARK(4);
     // ---- ctx = P v: thread = (head, dim), V read from its buffer
-    ATP_TS(4);
     mbar_wait(&v_full, k & 1);
-    ATP_TS(5);
     for (int c = tid; c < D_MODEL; c += NT) {
       const int h = c / D_HEAD;
       const float* vcol = reinterpret_cast<const float*>(vbuf) + c;
@@ -991,14 +976,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2) attention_pipe_kernel(c
         if (t < T) a.ctx[(size_t)(b * T + t) * D_MODEL + c] = __float2bfloat16(acc[t]);
     }
     __syncthreads();                                         // the v buffer and ps are free again
-    ATP_TS(6);
     if (warp == 0 && k + 1 < nmine) issue_v(k + 1);
   }
-#ifdef TONE_PROF
-  if (blockIdx.x == 0 && tid == 0 && g_prof)
-    printf("attn pipe T %d Tk %d: wait_kq %lld ln %lld scores %lld softmax %lld wait_v %lld pv %lld\n", T, Tk, tp[1] - tp[0], tp[2] - tp[1],
-           tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], tp[6] - tp[5]);
-#endif
   PROF_END();
 }
 

@@ -165,13 +165,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_pair_kernel(const __gri
     mbar_wait(acc_full, 0);
     if (threadIdx.x == 64) PROF_MARK(4);
     tc_fence_after();
-#ifdef TONE_PROF
-    long long tq[6];
-    tq[0] = clock64();
-#define RG_TS(i) tq[i] = clock64()
-#else
-#define RG_TS(i)
-#endif
     // Phase A (thread = row, columns [192 hf, +192)): scale * (acc + b) -> fp32 tile X[128][388] over the dead ring
     float* X = reinterpret_cast<float*>(smem);
     {
@@ -194,9 +187,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_pair_kernel(const __gri
         }
       }
     }
-    RG_TS(1);
     bar_epilogue();
-    RG_TS(2);
     // Phase B (warp = 16 rows, lanes along the row, 8 rows in flight)
     Vec384 g1v, g2v;
 #pragma unroll
@@ -209,7 +200,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_pair_kernel(const __gri
     // only two warps share a scheduler, so walking them one row at a time leaves the SM waiting on latencies.
 #pragma unroll 1
     for (int rg = 0; rg < 16; rg += 8) {
-      if (rg) { RG_TS(3); load_rows(rg); }
+      if (rg) load_rows(rg);
       bool ok[8];
       float inv[8];
 #pragma unroll
@@ -294,12 +285,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_pair_kernel(const __gri
         }
       }
     }
-#ifdef TONE_PROF
-      if (threadIdx.x == 64 && blockIdx.x == 0 && g_prof) {
-      tq[4] = clock64();
-      printf("rowgemm nk %d: phaseA %lld bar %lld rows0-7 %lld rows8-15 %lld\n", a.nk, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3]);
-    }
-#endif
   }
   tc_fence_before();
   pair_sync_all();
