@@ -581,7 +581,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
   e->persist_ctas = e->num_sms;
   e->lane_ctas = cfg->persist_ctas > 0 ? std::min(cfg->persist_ctas, e->num_sms) : e->num_sms;
   e->persist_min_tiles = cfg->persist_min_tiles < 0 ? 0 : (cfg->persist_min_tiles ? cfg->persist_min_tiles : e->num_sms + 1);
-  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(cudaFuncSetAttribute(begin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
   CK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_V_SMEM));
   CK(cudaFuncSetAttribute(attention_pipe_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
   CK(cudaFuncSetAttribute(attention_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -1318,7 +1318,8 @@ static int run_step(tone_engine* e, tone_engine::Lane& ln, int B, cudaStream_t s
     a.T2 = T2;
     a.B = B;
     const int n_mt = (F + 15) / 16, UH = ((16 * n_mt * HOP + HOP + 16) + 7) & ~7;
-    const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + ROLL_BYTES + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4;
+    const size_t smem = (size_t)2 * BASIS_N * BASIS_LD * 2 + ROLL_BYTES + (size_t)UH * 2 + (size_t)(F * 162 + F * N_MELS) * 4 +
+                        (size_t)C * 4 + HOP * 2;   // + staging of the next stream's PCM (int32 at most) and carried samples
     KLAUNCH(launch_kernel(begin_step_kernel, dim3(std::min(B, e->cur_ctas)), dim3(BEGIN_THREADS), smem, st, e->pdl, a));
   }
   {  // conv0: rows = F frames per stream, K = 11 kernel rows x 64 mel bins, N = 44 positions x 32 channels

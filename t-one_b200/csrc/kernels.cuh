@@ -101,10 +101,11 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   __half* uh = reinterpret_cast<__half*>(rollS + ROLL_BYTES);   // [UH] carried 80 samples + chunk, zero tail
   float* spec = reinterpret_cast<float*>(uh + ((UH + 7) & ~7));   // [F][162]
   float* featS = spec + F * 162;                        // [F][64]
+  unsigned char* pcmS = reinterpret_cast<unsigned char*>(featS + F * N_MELS);   // raw PCM of the NEXT stream | its 80 carried samples
   const int tid = threadIdx.x;
   // constant basis -> smem by ONE bulk async copy (113 KB), issued before the PDL wait and awaited just before the DFT;
   // the mel filterbank (CSR, ~1 KB) is staged the same way so that the mel loop does not chase indices in global memory
-  __shared__ uint64_t basis_bar, roll_bar;
+  __shared__ uint64_t basis_bar, roll_bar, pcm_bar;
   __shared__ int mel_startS[N_MELS + 1];
   __shared__ unsigned char mel_binS[256];
   __shared__ float mel_wS[256];
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   if (tid == 0) {
     mbar_init(&basis_bar, 1);
     mbar_init(&roll_bar, 1);
+    mbar_init(&pcm_bar, 1);
     fence_mbar_init();
     mbar_expect_tx(&basis_bar, BASIS_BYTES);
     bulk_load_1d(basisS, a.basis, BASIS_BYTES, &basis_bar);
@@ -130,6 +132,16 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
   pdl_wait();
   if (threadIdx.x == 0) PROF_MARK(2);
 
+  // The waveform of a stream (its chunk of the batch's PCM, contiguous, and the 80 samples carried in the slot) is
+  // brought into shared memory by bulk async copies one stream ahead, so an iteration starts on data that is already
+  // on the SM instead of a slot-id -> address -> samples chain of global round trips.
+  const uint32_t pcm_bytes = (uint32_t)C * (a.pcm_fmt ? 2u : 4u);
+  auto fetch_pcm = [&](int b) {      // tid 0
+    mbar_expect_tx(&pcm_bar, pcm_bytes + HOP * 2);
+    bulk_load_1d(pcmS, reinterpret_cast<const unsigned char*>(a.pcm) + (size_t)b * pcm_bytes, pcm_bytes, &pcm_bar);
+    bulk_load_1d(pcmS + pcm_bytes, a.pre + (size_t)a.slots[b] * HOP, HOP * 2, &pcm_bar);
+  };
+  if (tid == 0 && !a.feats_in && (int)blockIdx.x < a.B) fetch_pcm(blockIdx.x);
   int iter = 0;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
   const int slot = a.slots[b];
@@ -151,18 +163,21 @@ __global__ void __launch_bounds__(BEGIN_THREADS) begin_step_kernel(const BeginAr
     if (tid < SUB1_ROWS * N_MELS / 8) f4[tid] = f4[F * N_MELS / 8 + tid];
     // ---- waveform: int -> /32767 -> fp16 (model.py:164-165), prefixed by the carried 80 samples (feats.py:129-133)
     __half* pre = a.pre + (size_t)slot * HOP;
-    const int* pcm32 = reinterpret_cast<const int*>(a.pcm) + (size_t)b * C;
-    const short* pcm16 = reinterpret_cast<const short*>(a.pcm) + (size_t)b * C;
     if (!a.feats_in) {
+      mbar_wait(&pcm_bar, iter & 1);
+      const int* pcm32 = reinterpret_cast<const int*>(pcmS);
+      const short* pcm16 = reinterpret_cast<const short*>(pcmS);
+      const __half* preS = reinterpret_cast<const __half*>(pcmS + pcm_bytes);
       for (int i = tid; i < UH; i += BEGIN_THREADS) {
         __half v = __float2half_rn(0.f);
-        if (i < HOP) v = pre[i];
+        if (i < HOP) v = preS[i];
         else if (i < C + HOP)
           v = __float2half_rn(static_cast<float>(a.pcm_fmt ? (int)pcm16[i - HOP] : pcm32[i - HOP]) / 32767.0f);
         uh[i] = v;
       }
     }
     __syncthreads();
+    if (tid == 0 && !a.feats_in && b + (int)gridDim.x < a.B) fetch_pcm(b + gridDim.x);   // the staging buffer is free again
     if (tid == 0) {
       int len = a.mhsa_len[slot];
       a.len_in[b] = len;
