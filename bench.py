@@ -36,6 +36,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 FLOP_PER_CHUNK = {2400: 1_287_738_880, 3200: 1_631_636_224}   # SURVEY.md §8d / BASELINE.md §4 (2 x MAC, reference graph)
 METRIC = "streaming RTFx (audio-sec/sec)"

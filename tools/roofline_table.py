@@ -29,23 +29,32 @@ def main():
     F = lambda m, n, k: 2.0 * m * n * k                             # noqa: E731
     table = [
         # (regex on name, grid, label, FLOP, HBM bytes)
-        (r"persist_kernel<2,", (148, 1, 1), "FF up + SwiGLU (persistent, 256-wide), rows 5120 | 2560 alternate", (F(R, 2 * DFF, D) + F(R2, 2 * DFF, D)) / 2, None),
-        (r"gemm_tc_kernel<8, 128", (40, 3, 1), "FF down (partial sums), 5120 rows", F(R, D, DFF), None),
+        (r"persist_kernel<2,", (120, 1, 1), "FF up + SwiGLU (persistent, 256-wide tiles), rows 5120 / 2560 alternate", (F(R, 2 * DFF, D) + F(R2, 2 * DFF, D)) / 2, None),
+        (r"gemm_tc_kernel<8, 128", (40, 3, 1), "FF2 down (fp16 partial sums), 5120 rows", F(R, D, DFF), None),
         (r"gemm_tc_kernel<8, 128", (20, 3, 2), "FF down (split-K 2), 2560 rows", F(R2, D, DFF), None),
-        (r"gemm_tc_kernel<1, 128", (40, 3, 1), "W_o / pw2 + residual, 5120 rows", F(R, D, D), None),
+        (r"gemm_tc_kernel<1, 128", (40, 3, 1), "W_o / pw2 (K = 384: 32 launches) and FF1 down (K = 1536: 14) + residual, 5120 rows", (32 * F(R, D, D) + 14 * F(R, D, DFF)) / 46, None),
         (r"gemm_tc_kernel<1, 128", (20, 3, 1), "W_o / pw2 + residual, 2560 rows", F(R2, D, D), None),
         (r"persist_kernel<3,", (120, 1, 1), "conv-module pw1 + GLU (persistent), 5120 rows", F(R, 2 * D, D), None),
         (r"gemm_tc_kernel<3, 128", (20, 6, 1), "conv-module pw1 + GLU, 2560 rows", F(R2, 2 * D, D), None),
-        (r"gemm_tc_kernel<0, 128", (40, 3, 1), "V / Q projection, 5120 rows", F(R, D, D), None),
-        (r"gemm_tc_kernel<0, 128", (20, 3, 1), "V / Q projection, 2560 rows", F(R2, D, D), None),
+        (r"gemm_tc_kernel<10, 48", (43, 8, 1), "V projection + P.V (one head per CTA), 5120 rows", F(R, D, D), None),
+        (r"gemm_tc_kernel<10, 48", (21, 8, 1), "V projection + P.V, 2560 rows", F(R2, D, D), None),
+        (r"gemm_tc_kernel<0, 128", (40, 3, 1), "Q projection (layers 14 / 15 full rate), 5120 rows", F(R, D, D), None),
+        (r"gemm_tc_kernel<0, 128", (20, 3, 1), "Q projection / reduction pointwise, 2560 rows", F(R2, D, D), None),
+        (r"persist_kernel<0, 1", (120, 1, 1), "q, k, v projection, layer 0 (N = 1152), 5120 rows", F(R, 3 * D, D), None),
+        (r"persist_kernel<0, 1", (90, 1, 1), "q, k, v projection, layer 7, 2560 rows", F(R2, 3 * D, D), None),
+        (r"gemm_tc_kernel<6, 128", (171, 6, 1), "K, V projection of [cache, new] rows, layer 15 (40 rows per stream)", F(S * 40, 2 * D, D), None),
+        (r"gemm_tc_kernel<6, 128", (86, 6, 1), "K, V projection, layer 14 (20 rows per stream)", F(S * 20, 2 * D, D), None),
         (r"gemm_tc_kernel<5, 128", (43, 17, 1), "conv1 implicit GEMM (K = 11 x 384), 512 streams", 2.0 * S * T * 34 * 64 * 32 * 121, None),
         (r"gemm_tc_kernel<4, 128", (128, 11, 1), "conv0 implicit GEMM (banded), 512 streams", 2.0 * S * 30 * 44 * 32 * 231, None),
         (r"norm_kernel", (640, 1, 1), "RMSNorm + partial fold, 5120 rows (r fp32 r/w, partial fp16, n bf16)", None, R * D * (4 + 4 + 2 + 2)),
         (r"norm_kernel", (320, 1, 1), "RMSNorm + partial fold, 2560 rows", None, R2 * D * (4 + 4 + 2 * 2 + 2)),
-        (r"dwconv_kernel<5>", (512, 2, 1), "depthwise conv k=31, T=10 (cache 30 rows r/w, g in, e out)", None, S * D * 2 * (30 + 30 + T + T)),
-        (r"dwconv_kernel<3>", (512, 2, 1), "depthwise conv k=31, T=5", None, S * D * 2 * (30 + 30 + T2 + T2)),
-        (r"attention_kernel<0>", (512, 1, 1), "P.V with shared scores (V fp32 in, P in, ctx bf16 out)", None, S * T * D * (4 + 2) + S * 8 * T * T * 4),
-        (r"begin_step_kernel", (512, 1, 1), "log-mel front end + cache rolls (PCM int16 in, 70 KB of rolls per stream)", None, S * (2400 * 2 + 2 * 70000)),
+        (r"dwconv_pipe_kernel<10>", (296, 1, 1), "depthwise conv k=31, T=10 (ring cache: 30 rows in, T rows out; g in, e out)", None, S * D * 2 * (30 + T + T + T)),
+        (r"dwconv_pipe_kernel<5>", (296, 1, 1), "depthwise conv k=31, T=5", None, S * D * 2 * (30 + T2 + T2 + T2)),
+        (r"attention_pipe_kernel<512>", (148, 1, 1), "cached-context attention, layers 14 / 15 (k, v fp32 in: 20 / 40 rows, q, P out, ctx out), average", None,
+         S * (30 * 2 * D * 4 + 1.5 * T2 * D * 4 + 8 * 7.5 * 30 * 4 + 7.5 * D * 2)),
+        (r"attention_pipe_kernel<256>", (296, 1, 1), "attention of layers 0 / 7 (q, k, v fp32 in, P out, ctx out), average", None,
+         S * (7.5 * 3 * D * 4 + 8 * (100 + 25) / 2 * 4 + 7.5 * D * 2)),
+        (r"begin_step_kernel", (148, 1, 1), "log-mel front end + cache rolls (PCM int16 in, 57 KB of rolls per stream)", None, S * (2400 * 2 + 2 * 57088 + 30 * 64 * 2)),
     ]
     agg = collections.OrderedDict()
     for l in launches.values():
@@ -59,7 +68,7 @@ def main():
     print("Algorithmic FLOPs (GEMM kinds) or algorithmic HBM bytes (bandwidth kernels) per launch / the launch's ncu duration "
           "(`profiles/r02_step_B1024.csv`: cold caches, serialised replay - a lower bound of the live rate), against the measured "
           f"burst peaks ({PEAK['bf16_tflops']:.0f} TFLOP/s bf16, {PEAK['hbm_gbs']:.0f} GB/s; `MEASURED_PEAKS.json`).  The whole step, "
-          "timed live by `bench.py`, runs at 450 TFLOP/s = 31.9 % of the sustained peak (1412.7).\n")
+          "timed live by `bench.py`, runs at 498 TFLOP/s = 35.3 % of the sustained peak (1412.7).\n")
     print("| kernel | launches | avg us | algorithmic work per launch | achieved | of measured peak |")
     print("|---|---|---|---|---|---|")
     for label, (n, us, flop, byts) in agg.items():
