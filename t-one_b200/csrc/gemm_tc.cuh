@@ -1386,13 +1386,14 @@ inline cudaError_t launch_gemm_tc_persist(cudaStream_t st, const CUtensorMap& tm
   return cudaLaunchKernelEx(&cfg, gemm_tc_persist_kernel<KIND, NSUB, PAIR>, tmA, tmB, a, tiles_y, ntiles);
 }
 
-// deep = one CTA per SM, whole smem as the ring (grids that fit in one wave); otherwise two CTAs per SM.
+// deep = one CTA per SM, whole smem as the ring (grids that fit in one wave of single CTAs); otherwise two CTAs per SM
+// (a grid of 149 .. 296 CTAs then still runs in one round instead of one full round plus a nearly empty one).
 template <int KIND, int BN>
 inline cudaError_t launch_gemm_tc(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmAw,
                                   const CUtensorMap& tmB, const GemmArgs& a, int m_tiles, int n_tiles, bool pdl,
                                   int num_sms, int splits = 1) {
   const dim3 grid(m_tiles, n_tiles, splits);
-  if (m_tiles * n_tiles * splits <= 2 * num_sms)
+  if (m_tiles * n_tiles * splits <= num_sms)
     return launch_kernel(gemm_tc_kernel<KIND, BN, true>, grid, dim3(GEMM_THREADS), TileCfg<BN, true>::SMEM_BYTES, st, pdl, tmA,
                          tmAw, tmB, a);
   return launch_kernel(gemm_tc_kernel<KIND, BN, false>, grid, dim3(GEMM_THREADS), TileCfg<BN, false>::SMEM_BYTES, st, pdl, tmA,
