@@ -231,6 +231,7 @@ struct tone_engine {
   int persist_min_tiles = 0, persist_ctas = 0;
   int lane_ctas = 0;    // persistent-kernel CTAs while a step runs in more than one lane (tone_config.persist_ctas)
   int cur_ctas = 148;   // CTAs a persistent kernel of the step being enqueued may occupy
+  int cur_lanes = 1;    // lanes of the step being enqueued
   // gated kinds (N % 256 == 0): 0 = 128-wide tiles, 1 = 256-wide, 2 = 256-wide on CTA pairs (cta_group::2).  Measured
   // (profiles/r01_persistent_gemm.md): the pair form runs the feed-forward up GEMM at 73 % of the sustained bf16 peak when
   // it has the GPU to itself, but with two lanes in flight the 256-wide single-CTA form gives the faster step.
@@ -552,6 +553,7 @@ static int create_impl(tone_engine* e, const tone_config* cfg, const cudaDeviceP
 
   CK((configure_gemm_tc<G_SWIGLU, BN_SWIGLU>()));
   CK((configure_gemm_tc<G_RESID, BN_RESID>()));
+  CK((configure_gemm_tc<G_RESID, 64>()));
   CK((configure_gemm_tc<G_GLU, BN_GLU>()));
   CK((configure_gemm_tc<G_STORE_F32, BN_STORE>()));
   CK((configure_gemm_tc<G_STORE_F32, 32>()));
@@ -1078,7 +1080,7 @@ extern "C" int tone_release_slots(tone_engine* e, int32_t n, const int32_t* slot
 template <int KIND, int BN>
 static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const WeightMat& w, GemmArgs a, int m_tiles,
                 int n_tiles, int ref_rows, int ref_cols, const CUtensorMap* tmAw = nullptr, int splits = 1,
-                bool box128 = false) {
+                int box = 0) {   // weight map: 0 = w.map (box rows = the matrix's upload width), 1 = map128, 2 = map64
   a.W = w.ptr;
   a.ldw = w.K;
   cudaError_t err;
@@ -1090,7 +1092,7 @@ static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const W
               m_tiles * n_tiles >= std::min(e->persist_min_tiles, e->cur_ctas + 1);
   if (persist) {
     if constexpr (can_persist) {
-      const CUtensorMap& mb = box128 ? w.map128 : w.map;
+      const CUtensorMap& mb = box == 1 ? w.map128 : w.map;
       constexpr bool wide = (KIND == G_SWIGLU || KIND == G_GLU);   // N a multiple of 256: two weight tiles per tile
       if (wide && e->persist_mode == 2)
         err = launch_gemm_tc_persist<KIND, wide ? 2 : 1, wide>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->cur_ctas);
@@ -1099,7 +1101,7 @@ static int gemm(tone_engine* e, cudaStream_t st, const CUtensorMap& tmA, const W
       else err = launch_gemm_tc_persist<KIND, 1, false>(st, tmA, mb, a, m_tiles, n_tiles, e->pdl, e->cur_ctas);
     }
   } else if (e->cfg.gemm_impl == 0)
-    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, box128 ? w.map128 : w.map, a, m_tiles, n_tiles, e->pdl,
+    err = launch_gemm_tc<KIND, BN>(st, tmA, tmAw ? *tmAw : tmA, box == 1 ? w.map128 : (box == 2 ? w.map64 : w.map), a, m_tiles, n_tiles, e->pdl,
                                    e->num_sms, splits);
   else err = launch_gemm_ref<KIND, BN>(st, a, ref_rows, ref_cols, splits);
   e->launches++;
@@ -1232,7 +1234,12 @@ static int run_resid_rowscale(tone_engine* e, tone_engine::Lane& ln, cudaStream_
     a.rb_out = ln.rb;
     a.ss_out = ln.ss;
     a.ss_ld = 12;
-    if (M >= BIG_M) {
+    if (M >= BIG_M && e->cur_lanes == 1 && 2 * mt * (D_MODEL / 128) <= e->num_sms) {
+      // 128-wide tiles would fill at most half of the SMs (2560 rows: 60 CTAs): 64-wide tiles, half the epilogue per CTA
+      // (with two lanes the 60-CTA kernels of both lanes run side by side instead: measured equal or better)
+      *ss_tiles = D_MODEL / 64;
+      RC((gemm<G_RESID, 64>(e, st, mapA, w, a, mt, D_MODEL / 64, M, D_MODEL, nullptr, 1, 2)));
+    } else if (M >= BIG_M) {
       *ss_tiles = D_MODEL / 128;
       RC((gemm<G_RESID, 128>(e, st, mapA, w, a, mt, D_MODEL / 128, M, D_MODEL, nullptr, 1, true)));
     } else {
@@ -1660,6 +1667,7 @@ static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStrea
   int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
   nl = std::min(nl, B);
   e->cur_ctas = nl > 1 ? e->lane_ctas : e->num_sms;
+  e->cur_lanes = nl;
   e->launches = 0;
   const int per = (B + nl - 1) / nl;
   const int pcm_fmt = (mode & SM_PCM16) ? 1 : 0;
