@@ -73,7 +73,8 @@ typedef struct tone_config {
   int32_t use_graph;     /* 1 = replay a captured CUDA graph per batch size, 0 = eager       */
   /* ---- tuning (0 = default) */
   int32_t lanes;             /* concurrent sub-batches a large step is cut into (1..4; default 2)           */
-  int32_t lane_min_batch;    /* streams per lane below which the batch is not cut (default 384)              */
+  int32_t lane_min_batch;    /* streams per lane below which the batch is not cut (default: cut when one     */
+                             /* lane's 384-column GEMMs exceed one tile per SM, i.e. from 628 streams x 10 frames) */
   int32_t persist_min_tiles; /* dense GEMMs with at least this many 128x128 tiles run as the persistent      */
                              /* kernel (default: SM count + 1; -1 = never)                                   */
   int32_t persist_mode;      /* gated persistent GEMMs: 1 = 128-wide tiles, 2 = 256-wide (default),          */

@@ -217,7 +217,11 @@ struct tone_engine {
     float* aux_out;
   };
   std::vector<Lane> lanes;
-  int n_lanes = 2, lane_min_batch = 384;   // measured: lanes pay from ~768 streams (512 streams: 1.815 ms in one lane, 1.860 in two)
+  // Lanes: a step is cut into concurrent sub-batches when one lane's N = 384 GEMMs (3 column tiles per 128-row tile) no
+  // longer fit in one round of single-tile CTAs - 576 streams x 10 frames = 135 tiles run in one lane (1.66 ms; two lanes
+  // 1.91 ms), 640 streams = 150 tiles run in two (1.92 ms; one lane 2.15 ms).  tone_config.lane_min_batch > 0 replaces the
+  // rule by a fixed streams-per-lane threshold.
+  int n_lanes = 2, lane_min_batch = 0;
   cudaEvent_t fork_ev = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined step
   cudaStream_t s_cap = nullptr;                   // graph capture happens on a stream of its own
@@ -1664,7 +1668,11 @@ enum StepMode : int { SM_FEATURES = 1, SM_PHRASES = 2, SM_PCM16 = 4 };
 // a fork event and per-lane join events (works both eagerly and under stream capture).  Inputs / outputs are those of
 // staging set `io`.
 static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStream_t st, float* taps, int mode) {
-  int nl = taps ? 1 : std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
+  int nl = 1;
+  if (!taps) {
+    if (e->lane_min_batch > 0) nl = std::min(e->n_lanes, std::max(1, B / e->lane_min_batch));
+    else if (((B * e->T + 127) / 128) * (D_MODEL / 128) > e->num_sms) nl = e->n_lanes;
+  }
   nl = std::min(nl, B);
   e->cur_ctas = nl > 1 ? e->lane_ctas : e->num_sms;
   e->cur_lanes = nl;
