@@ -142,7 +142,7 @@ def test_step_matches_oracle(engines, weights, tb, C, B, n):
         eng.release_slots(slots)
 
 
-# ---- large-batch paths: 128-wide tiles (>= 2048 rows per lane), two concurrent lanes (>= 512 streams), and the
+# ---- large-batch paths: 128-wide tiles (>= 2048 rows per lane), two concurrent lanes (from 628 streams), and the
 # persistent GEMM kernel.  Streams are independent, so B streams that replay a handful of distinct signals must all
 # reproduce the oracle's answer for their signal (size-independent property; the oracle runs the distinct signals only).
 @pytest.mark.parametrize("C,B,persist,mode,ff", [(2400, 600, 0, 0, (0, 0)), (2400, 600, -1, 1, (1, 0)), (2400, 600, 1, 1, (1, 0)),
@@ -177,6 +177,36 @@ def test_large_batch_paths_match_oracle(weights, tb, C, B, persist, mode, ff):
         assert np.abs(got - flat_ref[idx[probe]]).max() <= ST_TOL
     finally:
         eng.close()
+
+
+# ---- the lane rule: a step is cut into two concurrent lanes when one lane's 384-column GEMMs exceed one 128 x 128 tile
+# per SM (ceil(B T / 128) * 3 > 148): 576 streams x 10 frames = 135 tiles -> one lane, 640 streams = 150 tiles -> two lanes
+# of 320 (3200-row lanes: a size no other test runs).  Both sides of the boundary must reproduce the oracle.
+def test_lane_rule_follows_the_tile_count_and_both_sides_match_oracle(weights, tb):
+    C, n, D = 2400, 3, 6
+    W = orc.to_torch(weights)
+    distinct = tb.synth.telephony_pcm(D, C * n, seed=79)
+    ref, st = _stream_oracle(W, distinct, C)
+    launches = {}
+    for B in (576, 640):
+        eng = tb.Engine(weights, chunk_samples=C, max_slots=B, max_batch=B)
+        try:
+            idx = (np.arange(B) * 7) % D
+            pcm = np.ascontiguousarray(distinct[idx])
+            slots = eng.alloc_slots(B)
+            lp, tk = _stream_engine(eng, slots, pcm, C)
+            launches[B] = eng._get_info().launches_per_step
+            assert np.isfinite(lp).all()
+            assert _lp_close(lp, ref[:, idx])
+            assert (tk == lp.argmax(-1)).all()
+            _check_tokens(tk, ref[:, idx])
+            flat_ref = orc.pack_state(st).astype(np.float32)
+            probe = np.array([0, 1, B // 2 - 1, B // 2, B - 1])
+            got = eng.export_states(slots[probe]).astype(np.float32)
+            assert np.abs(got - flat_ref[idx[probe]]).max() <= ST_TOL
+        finally:
+            eng.close()
+    assert launches[576] < 200 and launches[640] >= 2 * launches[576] - 8, launches   # 184 kernels in one lane, 2 x 191 in two
 
 
 # ---- large-batch kernel forms added in round 2b, forced on at sizes the oracle check can afford: the fused attention
