@@ -52,13 +52,17 @@ def workload_config(streams: int, chunk: int) -> dict:
 
 
 def measured_traffic(streams: int, chunk: int):
-    """DRAM bytes of one step (dram__bytes_read.sum + dram__bytes_write.sum over the step's launches) from the committed
-    ncu capture of this workload, if there is one; ncu replays every launch with cold caches: an upper bound."""
-    for name in (f"r02_dram_traffic_B{streams}.json", f"r01_dram_traffic_B{streams}.json"):
+    """DRAM bytes of one step (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of this
+    workload, if there is one.  Preferred: the LIVE figure (`ncu --replay-mode app-range --cache-control none` over a range
+    of consecutive steps: warm caches, lanes concurrent; tools/summarize_range.py).  Fallback: the sum over the per-launch
+    replay list, where ncu runs every kernel alone with cold caches - an upper bound of the reads."""
+    for name, how in ((f"r02_dram_live_B{streams}.json", "live range of consecutive steps, ncu --replay-mode app-range, warm caches"),
+                      (f"r02_dram_traffic_B{streams}.json", "sum over ncu's per-launch cold-cache replay"),
+                      (f"r01_dram_traffic_B{streams}.json", "sum over ncu's per-launch cold-cache replay")):
         p = os.path.join(ROOT, "profiles", name)
         if chunk == 2400 and os.path.exists(p):
             with open(p) as f:
-                return float(json.load(f)["dram_total_bytes"]), name
+                return float(json.load(f)["dram_total_bytes"]), f"{name}: {how}"
     return None, None
 
 
@@ -417,7 +421,7 @@ def run_ours(args):
             "launches_per_step": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"], "traffic": traffic,
-                         "traffic_note": (f"DRAM bytes per step launch, ncu cold-cache replay (profiles/{traffic_src}); " if traffic else "")
+                         "traffic_note": (f"DRAM bytes per step launch (profiles/{traffic_src}); " if traffic else "")
                                          + f"algorithmic: {info['weight_bytes'] / 1e6:.0f} MB weights + {B * 889_916 / 1e6:.0f} MB state/io",
                          "peak_source": peaks["src"],
                          "kernel": f"whole step graph (one launch = one {B}-stream step, {launches} kernels); per-kernel shares, "
