@@ -14,6 +14,7 @@
 // begin_step_kernel rolls them to the front.  Import/export use the same convention.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -34,6 +35,15 @@
 #include "att_fused.cuh"
 #include "rowgemm.cuh"
 #include "state_io.cuh"
+
+// NVTX ranges around the host side of every entry point that enqueues GPU work (visible in Nsight tools, filterable with
+// `ncu --nvtx --nvtx-include "tone_step_graph/"`); header-only NVTX 3: a no-op costing nanoseconds when no tool is attached.
+struct NvtxScope {
+  explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+  NvtxScope(const NvtxScope&) = delete;
+  NvtxScope& operator=(const NvtxScope&) = delete;
+};
 
 using namespace tone;
 
@@ -1725,11 +1735,13 @@ static int enqueue_step(tone_engine* e, tone_engine::IoSet& io, int B, cudaStrea
 // Replay (or capture on first use) the step graph of (batch size, staging set, mode) on `st`.
 static int launch_step(tone_engine* e, int set, int B, cudaStream_t st, int mode) {
   tone_engine::IoSet& io = e->io[set];
+  NvtxScope nvtx_("tone_step_graph");
   if (!e->cfg.use_graph) return enqueue_step(e, io, B, st, nullptr, mode);
   const uint64_t key = (uint64_t)B | ((uint64_t)set << 24) | ((uint64_t)mode << 28);
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     // Capture on a side stream that has nothing in flight, so the capture neither depends on nor disturbs `st`.
+    NvtxScope nvtx_cap("tone_step_capture");
     cudaGraph_t graph = nullptr;
     cudaStream_t cs = e->s_cap;
     CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
@@ -1799,6 +1811,7 @@ extern "C" int tone_next_staging(tone_engine* e, int32_t** slots, int16_t** pcm1
 
 extern "C" int tone_submit(tone_engine* e, int32_t B, const int32_t* slots, const void* pcm, int32_t pcm_format,
                            const uint8_t* is_last, int32_t outputs, int32_t* ticket_out) {
+  NvtxScope nvtx_("tone_submit");
   RC(check_step_args(e, B));
   if (!slots || !pcm || !ticket_out) return fail(TONE_EINVAL, "null argument");
   if (pcm_format != TONE_PCM_I32 && pcm_format != TONE_PCM_I16) return fail(TONE_EINVAL, "unknown pcm_format %d", pcm_format);
@@ -1850,6 +1863,7 @@ extern "C" int tone_submit(tone_engine* e, int32_t B, const int32_t* slots, cons
 }
 
 extern "C" int tone_wait(tone_engine* e, int32_t ticket, float* logprobs, int32_t* tokens, float* sil) {
+  NvtxScope nvtx_("tone_wait");
   if (!e) return fail(TONE_EINVAL, "null engine");
   tone_engine::IoSet* io = nullptr;
   for (int k = 0; k < tone_engine::PIPE; ++k)
@@ -1908,6 +1922,7 @@ extern "C" int tone_step(tone_engine* e, int32_t B, const int32_t* slots, const 
 
 // ------------------------------------------------------------------------------------------------ staged / device forms
 extern "C" int tone_stage(tone_engine* e, int32_t B, const int32_t* slots, const int32_t* pcm) {
+  NvtxScope nvtx_("tone_stage");
   RC(check_step_args(e, B));
   if (!slots || !pcm) return fail(TONE_EINVAL, "null argument");
   CK(cudaSetDevice(e->cfg.device));
@@ -1924,6 +1939,7 @@ extern "C" int tone_stage(tone_engine* e, int32_t B, const int32_t* slots, const
 }
 
 extern "C" int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream) {
+  NvtxScope nvtx_("tone_step_staged");
   RC(check_step_args(e, B));
   CK(cudaSetDevice(e->cfg.device));
   tone_engine::IoSet& io = legacy_set(e);
@@ -1938,6 +1954,7 @@ extern "C" int tone_step_staged(tone_engine* e, int32_t B, void* cuda_stream) {
 // staging (the captured graph reads fixed addresses), outputs are copied out the same way.  Stream-ordered, no sync.
 extern "C" int tone_step_device(tone_engine* e, int32_t B, const int32_t* slots, const void* d_pcm, int32_t pcm_format,
                                 float* d_logprobs, int32_t* d_tokens, void* cuda_stream) {
+  NvtxScope nvtx_("tone_step_device");
   RC(check_step_args(e, B));
   if (!slots) return fail(TONE_EINVAL, "null argument");
   if (pcm_format != TONE_PCM_I32 && pcm_format != TONE_PCM_I16) return fail(TONE_EINVAL, "unknown pcm_format %d", pcm_format);
@@ -2005,6 +2022,7 @@ extern "C" int tone_sync(tone_engine* e) {
 // features, triton/preprocessing/1/features_8k_tone.py): feats = host fp16 [B][64][F], F = chunk_samples / 80.
 extern "C" int tone_step_features(tone_engine* e, int32_t B, const int32_t* slots, const uint16_t* feats,
                                   float* logprobs, int32_t* tokens) {
+  NvtxScope nvtx_("tone_step_features");
   RC(check_step_args(e, B));
   if (!slots || !feats) return fail(TONE_EINVAL, "null argument");
   CK(cudaSetDevice(e->cfg.device));
@@ -2078,6 +2096,7 @@ extern "C" int tone_selftest_phrases(tone_engine* e, int32_t B, const int32_t* s
 // sub1 (1,10,64) | sub2 (32,8,44) | reduction (384,1): gathered / scattered on the device (state_io.cuh), one kernel and
 // one copy per STATE_IO_CHUNK slots.  The phrase-splitter state is not part of the model state and is left untouched.
 extern "C" int tone_export_states(tone_engine* e, int32_t n, const int32_t* slots, uint16_t* out) {
+  NvtxScope nvtx_("tone_export_states");
   if (!e || !slots || !out || n < 0) return fail(TONE_EINVAL, "bad argument");
   CK(cudaSetDevice(e->cfg.device));
   RC(validate_slots(e, n, slots, false));
@@ -2095,6 +2114,7 @@ extern "C" int tone_export_states(tone_engine* e, int32_t n, const int32_t* slot
 }
 
 extern "C" int tone_import_states(tone_engine* e, int32_t n, const int32_t* slots, const uint16_t* in) {
+  NvtxScope nvtx_("tone_import_states");
   if (!e || !slots || !in || n < 0) return fail(TONE_EINVAL, "bad argument");
   CK(cudaSetDevice(e->cfg.device));
   RC(validate_slots(e, n, slots, false));
