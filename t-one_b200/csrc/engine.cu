@@ -23,6 +23,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1781,8 +1782,9 @@ static int splice_end(tone_engine* e, cudaStream_t st) {
   return 0;
 }
 
-// int32 samples -> the int16 wire format, range-checked (tone/onnx_wrapper.py:108-113)
-static int narrow_pcm(const int32_t* src, int16_t* dst, size_t n) {
+// int32 samples -> the int16 wire format, range-checked (tone/onnx_wrapper.py:108-113).  Large batches (the synchronous
+// reference-shaped call at 1024 streams narrows 2.4 M samples) are cut across a few host threads.
+static void narrow_span(const int32_t* src, int16_t* dst, size_t n, int32_t* lo_out, int32_t* hi_out) {
   int32_t lo = n ? src[0] : 0, hi = lo;
   for (size_t i = 0; i < n; ++i) {
     const int32_t v = src[i];
@@ -1790,8 +1792,35 @@ static int narrow_pcm(const int32_t* src, int16_t* dst, size_t n) {
     hi = v > hi ? v : hi;
     dst[i] = (int16_t)v;
   }
-  if (lo < -32768 || hi > 32767)
-    return fail(TONE_ERANGE, "Samples in 'audio_chunk' must be in range [-32768; 32767], but it is in range [%d; %d]", (int)lo, (int)hi);
+  *lo_out = lo;
+  *hi_out = hi;
+}
+static int narrow_pcm(const int32_t* src, int16_t* dst, size_t n) {
+  constexpr int NT = 4;
+  int32_t lo[NT], hi[NT];
+  int used = 1;
+  if (n >= (size_t)1 << 19) {
+    const size_t per = (n + NT - 1) / NT;
+    std::thread th[NT - 1];
+    for (int t = 1; t < NT; ++t) {
+      const size_t a = std::min(n, t * per), b = std::min(n, (t + 1) * per);
+      th[t - 1] = std::thread(narrow_span, src + a, dst + a, b - a, &lo[t], &hi[t]);
+    }
+    narrow_span(src, dst, std::min(n, per), &lo[0], &hi[0]);
+    for (int t = 1; t < NT; ++t) th[t - 1].join();
+    used = NT;
+  } else {
+    narrow_span(src, dst, n, &lo[0], &hi[0]);
+  }
+  int32_t l = lo[0], h = hi[0];
+  for (int t = 1; t < used; ++t) {
+    const size_t a = std::min(n, t * ((n + NT - 1) / NT));
+    if (a >= n) continue;             // empty span: its lo / hi are the zero defaults of an empty range
+    l = std::min(l, lo[t]);
+    h = std::max(h, hi[t]);
+  }
+  if (l < -32768 || h > 32767)
+    return fail(TONE_ERANGE, "Samples in 'audio_chunk' must be in range [-32768; 32767], but it is in range [%d; %d]", (int)l, (int)h);
   return 0;
 }
 
