@@ -1802,12 +1802,21 @@ static int narrow_pcm(const int32_t* src, int16_t* dst, size_t n) {
   if (n >= (size_t)1 << 19) {
     const size_t per = (n + NT - 1) / NT;
     std::thread th[NT - 1];
-    for (int t = 1; t < NT; ++t) {
-      const size_t a = std::min(n, t * per), b = std::min(n, (t + 1) * per);
-      th[t - 1] = std::thread(narrow_span, src + a, dst + a, b - a, &lo[t], &hi[t]);
+    int started = 0;
+    try {
+      for (int t = 1; t < NT; ++t) {
+        const size_t a = std::min(n, t * per), b = std::min(n, (t + 1) * per);
+        th[t - 1] = std::thread(narrow_span, src + a, dst + a, b - a, &lo[t], &hi[t]);
+        ++started;
+      }
+    } catch (...) {   // no more threads to be had: this thread does the remaining spans itself
     }
     narrow_span(src, dst, std::min(n, per), &lo[0], &hi[0]);
-    for (int t = 1; t < NT; ++t) th[t - 1].join();
+    for (int t = started + 1; t < NT; ++t) {
+      const size_t a = std::min(n, t * per), b = std::min(n, (t + 1) * per);
+      narrow_span(src + a, dst + a, b - a, &lo[t], &hi[t]);
+    }
+    for (int t = 1; t <= started; ++t) th[t - 1].join();
     used = NT;
   } else {
     narrow_span(src, dst, n, &lo[0], &hi[0]);
